@@ -1,0 +1,239 @@
+/*
+ * rst_align.h — C ABI of the B200-native RGB-D frame alignment engine.
+ *
+ * This is the drop-in boundary for the reference's `rs_tracker/align` hot path.
+ * Citations are relative to the reference tree (yycho0108/RealsenseTracker):
+ *
+ *   - `bool AlignIcp3d(const Cloud3f& src, const Cloud3f& dst, int max_iter,
+ *      Eigen::Isometry3f* transform)`
+ *        rs_tracker/align/include/rs_tracker/align/align_icp.hpp:19-24
+ *        rs_tracker/align/src/align_icp.cpp:73-167
+ *     -> the pose is READ as the initial guess and OVERWRITTEN with the result
+ *        (align_icp.cpp:82,156); it maps src -> dst: p_dst ~ T * p_src
+ *        (align_icp.cpp:107).  Every rst_align_* call keeps exactly that
+ *        contract (`poses_inout`).
+ *   - frame-level inputs come from the driver boundary
+ *        rs_tracker/driver/include/rs_tracker/driver/rs_driver.hpp:17-22
+ *     depth `CV_16UC1` row-major (rs_driver.cpp:211-212), intrinsics as the
+ *     3x3 K = [[fx,0,cx],[0,fy,cy],[0,0,1]] (rs_driver.cpp:264-280).
+ *   - failure convention: `false` for < 3 usable points (align_icp.cpp:77-79),
+ *     non-finite -> failure (align_gicp.cpp:146-151).  Here: per-pair
+ *     `rst_stats.status != RST_STATUS_OK`; the C++ wrapper maps it to `bool`.
+ *
+ * No C++ types, no exceptions, no ownership transfer: the caller allocates all
+ * outputs.  One context per GPU; a context is not thread-safe, different
+ * contexts are independent (the reference is stateless / re-entrant).
+ *
+ * There is NO CPU fallback behind this ABI.  Every compute entry point fails
+ * with RST_ERR_CUDA / RST_ERR_NO_DEVICE when no sm_100 device is usable.
+ */
+#ifndef RST_ALIGN_H_
+#define RST_ALIGN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RST_ABI_VERSION 1
+#define RST_MAX_LEVELS 4
+
+/* ---- return codes of the API calls (call-level, not per-pair) ---- */
+enum {
+  RST_OK = 0,
+  RST_ERR_INVALID_ARG = 1,  /* null pointer, bad size, bad params          */
+  RST_ERR_NO_DEVICE = 2,    /* no CUDA device / device id out of range     */
+  RST_ERR_CUDA = 3,         /* a CUDA runtime call failed (see last_error) */
+  RST_ERR_CAPACITY = 4,     /* more frames/pairs/pixels than the ctx holds */
+  RST_ERR_ALIGNMENT = 5,    /* device input violates the pitch/alignment rule */
+  RST_ERR_ARCH = 6          /* device is not sm_100 (B200)                 */
+};
+
+/* ---- per-pair status word (rst_stats.status), sticky over iterations ---- */
+enum {
+  RST_STATUS_OK = 0,
+  RST_STATUS_TOO_FEW = 1,    /* fewer than params.min_count associations
+                                (reference: "< 3 points -> false")          */
+  RST_STATUS_DEGENERATE = 2, /* 6x6 Cholesky hit a non-positive pivot       */
+  RST_STATUS_NON_FINITE = 4  /* NaN/Inf in the normal equations or the pose */
+};
+
+/* ---- robust weight kinds (rst_params.robust_kind) ---- */
+enum {
+  RST_ROBUST_NONE = 0,
+  RST_ROBUST_HUBER = 1,          /* w = min(1, delta/|r|)   (ceres::HuberLoss,
+                                    align_gicp.cpp:67)                       */
+  RST_ROBUST_GEMAN_MCCLURE = 2   /* w = (mu/(r^2+mu))^2    (align_icp.cpp:116-118) */
+};
+
+/* Pin-hole intrinsics of the finest level; K = [[fx,0,cx],[0,fy,cy],[0,0,1]]
+ * (rs_driver.cpp:264-280).  No distortion. */
+typedef struct rst_intrinsics {
+  float fx, fy, cx, cy;
+} rst_intrinsics;
+
+/* One depth frame (host or device memory depending on the call).
+ * depth: uint16 row-major, 0 = invalid (CV_16UC1, rs_driver.cpp:211).
+ * rgb:   optional uint8 RGB, 3 bytes per pixel (CV_8UC3, rs_driver.cpp:212);
+ *        NULL when unused. Strides are in BYTES. */
+typedef struct rst_frame {
+  const uint16_t* depth;
+  const uint8_t* rgb;
+  int32_t width, height;
+  int32_t depth_stride_bytes;
+  int32_t rgb_stride_bytes;
+} rst_frame;
+
+/* Algorithm parameters (the reference hard-codes its constants,
+ * align_icp.cpp:91,96-98,165; here they are one POD). Fill with
+ * rst_params_default() and override. */
+typedef struct rst_params {
+  int32_t num_levels;             /* pyramid levels, 1..RST_MAX_LEVELS          */
+  int32_t iters[RST_MAX_LEVELS];  /* iterations per level, [0] = finest; run
+                                     coarse -> fine; fixed count, no early exit */
+  float depth_scale;              /* metres per depth LSB (D435: 0.001)         */
+  float z_min, z_max;             /* valid depth range in metres                */
+  float dist_max;                 /* association gate |p'-q| <= dist_max (m)    */
+  float normal_cos_min;           /* src/dst normal gate; <= -1 disables        */
+  float normal_depth_tol;         /* tau_n: |z_nbr - z| <= tau_n * z            */
+  int32_t pyr_depth_tol;          /* tau_pyr in LSB for the 2x2 depth pooling   */
+  int32_t robust_kind;            /* RST_ROBUST_*                               */
+  float robust_scale;             /* Huber delta (m) or Geman-McClure mu (m^2)  */
+  int32_t min_count;              /* minimum associations per iteration         */
+  float damping;                  /* added to diag(A) before the solve          */
+  float photo_weight;             /* lambda of the photometric term, 0 = off    */
+  int32_t reserved[4];
+} rst_params;
+
+/* Per-pair result statistics. A/b/sum_wr2/count belong to the LAST evaluated
+ * iterate, i.e. the correspondences BEFORE the final update — the same
+ * "pre-update" semantics as the reference's mean_cost (align_icp.cpp:104-113,157). */
+typedef struct rst_stats {
+  int32_t status;      /* RST_STATUS_* bit-or                                  */
+  int32_t iterations;  /* iterations executed                                   */
+  int32_t count;       /* associations in the last iteration                    */
+  float rmse;          /* sqrt(sum_wr2 / count) of the last iteration (m)       */
+  double sum_wr2;      /* sum w r^2                                             */
+  double A[21];        /* upper triangle of J^T W J, row-major (0,0)..(5,5)     */
+  double b[6];         /* J^T W r                                               */
+} rst_stats;
+
+typedef struct rst_ctx rst_ctx;
+
+/* -------------------------------------------------------------------------
+ * Context
+ * ---------------------------------------------------------------------- */
+
+/* Creates a context on CUDA device `device` able to hold `max_frames` frames of
+ * up to max_width x max_height and `max_pairs` pairs. `stream` is a
+ * cudaStream_t (or NULL to let the context create its own). */
+int32_t rst_ctx_create(int32_t device, int32_t max_width, int32_t max_height,
+                       int32_t max_frames, int32_t max_pairs, void* stream,
+                       rst_ctx** out_ctx);
+void rst_ctx_destroy(rst_ctx* ctx);
+
+/* Last error message of this context ("" if none). Never NULL. */
+const char* rst_last_error(const rst_ctx* ctx);
+/* Message of the last rst_ctx_create failure in this thread. */
+const char* rst_last_create_error(void);
+
+int32_t rst_abi_version(void);
+void rst_params_default(rst_params* params);
+
+/* -------------------------------------------------------------------------
+ * Alignment — host frames in, poses out (H2D and D2H inside the call).
+ * Replaces: AlignIcp3d(src, dst, max_iter, &T)  align_icp.cpp:163-167
+ *   pair i aligns src[i] onto dst[i]; poses_inout[16*i..] is a column-major
+ *   4x4 fp32 matrix (bit-compatible with Eigen::Isometry3f::matrix()).
+ * stats_out may be NULL.  Returns RST_OK when the batch ran; per-pair failure
+ * is in stats_out[i].status.
+ * ---------------------------------------------------------------------- */
+int32_t rst_align_pairs(rst_ctx* ctx, const rst_frame* src, const rst_frame* dst,
+                        int32_t n_pairs, const rst_intrinsics* intr,
+                        const rst_params* params, float* poses_inout,
+                        rst_stats* stats_out);
+
+/* Frame-to-frame odometry over a sequence (the loop of rs_replay_app.cpp:211-287):
+ * pair i aligns frames[i+1] (src, "curr") onto frames[i] (dst, "prev"), so
+ * poses_inout[16*i..] = T_{i <- i+1}; n_frames-1 pairs. Each frame is uploaded
+ * and pre-processed once. */
+int32_t rst_align_sequence(rst_ctx* ctx, const rst_frame* frames, int32_t n_frames,
+                           const rst_intrinsics* intr, const rst_params* params,
+                           float* poses_inout, rst_stats* stats_out);
+
+/* -------------------------------------------------------------------------
+ * Staged / device-resident interface (what the two calls above are built from;
+ * this is what an HBM-resident benchmark or a multi-stage host uses).
+ * ---------------------------------------------------------------------- */
+
+/* Declares the geometry of the frames that follow and resets the frame slots. */
+int32_t rst_begin(rst_ctx* ctx, int32_t width, int32_t height,
+                  const rst_intrinsics* intr, const rst_params* params);
+
+/* Copies host depth frames into slots [first_slot, first_slot+n). Asynchronous
+ * on the context stream when the host memory is pinned. */
+int32_t rst_upload_frames(rst_ctx* ctx, const rst_frame* frames, int32_t n,
+                          int32_t first_slot);
+
+/* Uses `n` depth frames already in device memory, laid out back to back:
+ * frame k starts at d_depth + k*frame_stride_px, rows are row_stride_px apart.
+ * Requires d_depth 16-byte aligned and row_stride_px, frame_stride_px multiples
+ * of 8 (RST_ERR_ALIGNMENT otherwise). The memory is read in place (level 0 is
+ * not copied) and must stay valid until the next rst_begin. */
+int32_t rst_set_frames_device(rst_ctx* ctx, const uint16_t* d_depth, int32_t n,
+                              int32_t row_stride_px, int64_t frame_stride_px,
+                              int32_t first_slot);
+
+/* Builds depth pyramid + geometry maps (K1+K2+K6) for slots [first_slot, first_slot+n). */
+int32_t rst_preprocess(rst_ctx* ctx, int32_t first_slot, int32_t n);
+
+/* Runs the coarse-to-fine ICP for n_pairs pairs; pair i = (src_slots[i] ->
+ * dst_slots[i]) (host int arrays). poses_inout / stats_out are HOST pointers,
+ * or NULL to leave the results on the device (see rst_device_results). The call
+ * is asynchronous w.r.t. the host unless results are requested. */
+int32_t rst_align_slots(rst_ctx* ctx, const int32_t* src_slots,
+                        const int32_t* dst_slots, int32_t n_pairs,
+                        float* poses_inout, rst_stats* stats_out);
+
+/* Device pointers of the result arrays of the last rst_align_slots:
+ * poses: n_pairs x 16 fp32 (column-major 4x4), stats: n_pairs x rst_stats. */
+int32_t rst_device_results(rst_ctx* ctx, const float** d_poses,
+                           const rst_stats** d_stats);
+
+/* Blocks until all work queued on the context stream has finished. */
+int32_t rst_sync(rst_ctx* ctx);
+
+/* -------------------------------------------------------------------------
+ * Single-stage entry points (parity tests and staged hosts).  All operate on
+ * the slots of the current rst_begin(); outputs are HOST pointers.
+ * ---------------------------------------------------------------------- */
+
+/* Level geometry: width/height/pitch (pixels) and intrinsics of pyramid level. */
+int32_t rst_level_info(const rst_ctx* ctx, int32_t level, int32_t* width,
+                       int32_t* height, int32_t* pitch_px, rst_intrinsics* intr);
+
+/* Reads back the depth pyramid level of a slot, densely packed width*height. */
+int32_t rst_read_depth(rst_ctx* ctx, int32_t slot, int32_t level, uint16_t* out);
+
+/* Reads back the geometry map of a slot/level: width*height float4
+ * {nx, ny, nz, z}; z = 0 where the vertex or the normal is invalid. */
+int32_t rst_read_geometry(rst_ctx* ctx, int32_t slot, int32_t level, float* out);
+
+/* One association + normal-equation evaluation at `level` under `pose`
+ * (column-major 4x4 fp32, src->dst), without updating any pose:
+ * idx_out[width*height] = dst pixel index v'*width+u' or -1 (may be NULL);
+ * stats_out gets A, b, sum_wr2, count of that evaluation. */
+int32_t rst_evaluate(rst_ctx* ctx, int32_t src_slot, int32_t dst_slot,
+                     int32_t level, const float* pose, int32_t* idx_out,
+                     rst_stats* stats_out);
+
+/* Number of kernel launches this context has issued so far (bench evidence). */
+int64_t rst_launch_count(const rst_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* RST_ALIGN_H_ */

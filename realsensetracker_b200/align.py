@@ -1,0 +1,193 @@
+"""Host-side mirror of the align interface over the C ABI (include/rst_align.h).
+
+Python here is only the test/bench harness language; the reference-facing host API is the
+C++ header include/rs_tracker/align/align_rgbd.hpp, which calls the same C ABI. Names and
+argument meaning follow the reference (`AlignIcp3d(src, dst, max_iter, &transform)`,
+align_icp.hpp:19-24): src -> dst pose, initial guess in, result out, bool success.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from ._native import Intrinsics, Params, Stats, Frame, RstError
+
+
+def default_params(**kw) -> Params:
+    p = Params()
+    N.align_lib().rst_params_default(C.byref(p))
+    for k, v in kw.items():
+        if k == "iters":
+            for i in range(N.RST_MAX_LEVELS):
+                p.iters[i] = v[i] if i < len(v) else 0
+        else:
+            if not hasattr(p, k):
+                raise AttributeError(k)
+            setattr(p, k, v)
+    return p
+
+
+def pose_to_cm(T) -> np.ndarray:
+    """[..,4,4] -> [..,16] column-major fp32 (bit-compatible with Eigen::Isometry3f::matrix())."""
+    T = np.asarray(T, dtype=np.float32)
+    return np.ascontiguousarray(np.swapaxes(T, -1, -2)).reshape(T.shape[:-2] + (16,))
+
+
+def cm_to_pose(p) -> np.ndarray:
+    p = np.asarray(p)
+    return np.swapaxes(p.reshape(p.shape[:-1] + (4, 4)), -1, -2).astype(np.float64)
+
+
+def _frames(arr: np.ndarray):
+    """numpy [n,h,w] uint16 (any row stride) -> (ctypes Frame array, keepalive)."""
+    assert arr.dtype == np.uint16 and arr.ndim == 3 and arr.strides[2] == 2
+    n, h, w = arr.shape
+    fr = (Frame * n)()
+    base = arr.ctypes.data
+    for i in range(n):
+        fr[i].depth = base + i * arr.strides[0]
+        fr[i].rgb = None
+        fr[i].width, fr[i].height = w, h
+        fr[i].depth_stride_bytes = arr.strides[1]
+        fr[i].rgb_stride_bytes = 0
+    return fr
+
+
+def stats_to_dict(s: Stats) -> dict:
+    return dict(status=s.status, iterations=s.iterations, count=s.count, rmse=s.rmse, sum_wr2=s.sum_wr2,
+                A=np.array(s.A[:]), b=np.array(s.b[:]))
+
+
+class Aligner:
+    """One alignment context on one GPU (rst_ctx). Not thread-safe; contexts are independent."""
+
+    def __init__(self, max_w: int, max_h: int, max_frames: int, max_pairs: int, device: int = 0, stream: int | None = None):
+        self._lib = N.align_lib()
+        self._ctx = C.c_void_p()
+        rc = self._lib.rst_ctx_create(device, max_w, max_h, max_frames, max_pairs, stream, C.byref(self._ctx))
+        if rc != N.RST_OK:
+            raise RstError(rc, self._lib.rst_last_create_error().decode())
+        self.max_frames, self.max_pairs = max_frames, max_pairs
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.rst_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != N.RST_OK:
+            raise RstError(rc, self._lib.rst_last_error(self._ctx).decode())
+
+    # ---- one-call API (host frames in, poses out) -------------------------------------------
+    def align_pairs(self, src: np.ndarray, dst: np.ndarray, intr, params: Params | None = None, T0=None):
+        """src, dst: [n,h,w] uint16. Returns (poses [n,4,4], list of Stats)."""
+        n = src.shape[0]
+        P = params if params is not None else default_params()
+        K = Intrinsics(*intr)
+        poses = pose_to_cm(np.broadcast_to(np.eye(4) if T0 is None else T0, (n, 4, 4))).copy()
+        stats = (Stats * n)()
+        self._check(self._lib.rst_align_pairs(self._ctx, _frames(src), _frames(dst), n, C.byref(K), C.byref(P),
+                                              poses.ctypes.data, C.addressof(stats)))
+        return cm_to_pose(poses), list(stats)
+
+    def align_sequence(self, frames: np.ndarray, intr, params: Params | None = None, T0=None):
+        """frames: [n,h,w] uint16; pair i aligns frames[i+1] onto frames[i]. Returns ([n-1,4,4], stats)."""
+        n = frames.shape[0]
+        P = params if params is not None else default_params()
+        K = Intrinsics(*intr)
+        poses = pose_to_cm(np.broadcast_to(np.eye(4) if T0 is None else T0, (n - 1, 4, 4))).copy()
+        stats = (Stats * (n - 1))()
+        self._check(self._lib.rst_align_sequence(self._ctx, _frames(frames), n, C.byref(K), C.byref(P),
+                                                 poses.ctypes.data, C.addressof(stats)))
+        return cm_to_pose(poses), list(stats)
+
+    # ---- staged API ---------------------------------------------------------------------------
+    def begin(self, w: int, h: int, intr, params: Params):
+        K = Intrinsics(*intr)
+        self._check(self._lib.rst_begin(self._ctx, w, h, C.byref(K), C.byref(params)))
+
+    def upload(self, frames: np.ndarray, first_slot: int = 0):
+        self._check(self._lib.rst_upload_frames(self._ctx, _frames(frames), frames.shape[0], first_slot))
+
+    def set_frames_device(self, dev_ptr: int, n: int, row_stride_px: int, frame_stride_px: int, first_slot: int = 0):
+        self._check(self._lib.rst_set_frames_device(self._ctx, dev_ptr, n, row_stride_px, frame_stride_px, first_slot))
+
+    def preprocess(self, first_slot: int, n: int):
+        self._check(self._lib.rst_preprocess(self._ctx, first_slot, n))
+
+    def align_slots(self, src_slots, dst_slots, T0=None, fetch: bool = True):
+        s = np.ascontiguousarray(src_slots, dtype=np.int32)
+        d = np.ascontiguousarray(dst_slots, dtype=np.int32)
+        n = len(s)
+        if not fetch:
+            assert T0 is None
+            self._check(self._lib.rst_align_slots(self._ctx, s.ctypes.data, d.ctypes.data, n, None, None))
+            return None, None
+        poses = pose_to_cm(np.broadcast_to(np.eye(4) if T0 is None else T0, (n, 4, 4))).copy()
+        stats = (Stats * n)()
+        self._check(self._lib.rst_align_slots(self._ctx, s.ctypes.data, d.ctypes.data, n, poses.ctypes.data,
+                                              C.addressof(stats)))
+        return cm_to_pose(poses), list(stats)
+
+    def sync(self):
+        self._check(self._lib.rst_sync(self._ctx))
+
+    def device_results(self):
+        dp, ds = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.rst_device_results(self._ctx, C.byref(dp), C.byref(ds)))
+        return dp.value, ds.value
+
+    def level_info(self, level: int):
+        w, h, p = C.c_int32(), C.c_int32(), C.c_int32()
+        K = Intrinsics()
+        self._check(self._lib.rst_level_info(self._ctx, level, C.byref(w), C.byref(h), C.byref(p), C.byref(K)))
+        return w.value, h.value, p.value, (K.fx, K.fy, K.cx, K.cy)
+
+    def read_depth(self, slot: int, level: int) -> np.ndarray:
+        w, h, _, _ = self.level_info(level)
+        out = np.empty((h, w), dtype=np.uint16)
+        self._check(self._lib.rst_read_depth(self._ctx, slot, level, out.ctypes.data))
+        return out
+
+    def read_geometry(self, slot: int, level: int) -> np.ndarray:
+        w, h, _, _ = self.level_info(level)
+        out = np.empty((h, w, 4), dtype=np.float32)
+        self._check(self._lib.rst_read_geometry(self._ctx, slot, level, out.ctypes.data))
+        return out
+
+    def evaluate(self, src_slot: int, dst_slot: int, level: int, T, want_idx: bool = True):
+        w, h, _, _ = self.level_info(level)
+        pose = pose_to_cm(T)
+        idx = np.empty((h, w), dtype=np.int32) if want_idx else None
+        st = Stats()
+        self._check(self._lib.rst_evaluate(self._ctx, src_slot, dst_slot, level, pose.ctypes.data,
+                                           idx.ctypes.data if want_idx else None, C.byref(st)))
+        return idx, st
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.rst_launch_count(self._ctx))
+
+
+def AlignRgbd(src_depth: np.ndarray, dst_depth: np.ndarray, K, params: Params | None = None, transform=None,
+              aligner: Aligner | None = None):
+    """Frame-based sibling of the reference's AlignIcp3d(src, dst, max_iter, &transform)
+    (align_icp.hpp:22-24): returns (success, transform 4x4, stats). `transform` is the initial
+    guess (identity if None), src -> dst."""
+    h, w = src_depth.shape
+    own = aligner is None
+    al = aligner or Aligner(w, h, 2, 1)
+    try:
+        T, st = al.align_pairs(src_depth[None], dst_depth[None], K, params, T0=transform)
+    finally:
+        if own:
+            al.close()
+    return st[0].status == N.RST_STATUS_OK, T[0], st[0]

@@ -1,0 +1,541 @@
+/*
+ * rst_capi.cu — the C ABI of include/rst_align.h over the sm_100a kernels.
+ * Host side of the drop-in boundary: context, HBM frame store, launch schedule.
+ * No CPU compute path exists here: every entry point either runs the CUDA kernels
+ * or returns an error code.
+ */
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rst_align.h"
+#include "rst_kernels.cuh"
+
+using namespace rst;
+
+struct rst_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int max_w = 0, max_h = 0, max_frames = 0, max_pairs = 0;
+
+  // geometry of the current rst_begin()
+  bool begun = false;
+  int w = 0, h = 0, num_levels = 0;
+  rst_intrinsics K{};
+  rst_params P{};
+  LevelGeom geom[RST_MAX_LEVELS]{};
+  int pitch[RST_MAX_LEVELS]{};
+  int64_t dframe[RST_MAX_LEVELS]{};
+  int64_t gframe[RST_MAX_LEVELS]{};
+  int blocks_per_pair[RST_MAX_LEVELS]{}, chunks_per_row[RST_MAX_LEVELS]{}, n_chunks[RST_MAX_LEVELS]{};
+
+  // HBM frame store (allocated once for max_w x max_h x max_frames)
+  uint16_t* d_depth[RST_MAX_LEVELS]{};
+  size_t depth_bytes[RST_MAX_LEVELS]{};
+  float4* d_geom[RST_MAX_LEVELS]{};
+  bool ext0 = false;  // level 0 read in place from caller memory
+  const uint16_t* ext_depth0 = nullptr;
+  int ext_pitch0 = 0;
+  int64_t ext_frame0 = 0;
+  bool store_dirty = true;
+
+  // pair state (max_pairs + 1: the last entry is the rst_evaluate scratch pair)
+  int2* d_pairs = nullptr;
+  float* d_poses_in = nullptr;
+  double* d_master = nullptr;
+  float* d_pose_f32 = nullptr;
+  float* d_poses_cm = nullptr;
+  rst_stats* d_stats = nullptr;
+  uint32_t* d_tickets = nullptr;
+  float* d_partials = nullptr;
+  int max_blocks = 0;
+  int32_t* d_idx = nullptr;
+  size_t idx_bytes = 0;
+
+  // pinned staging
+  int2* h_pairs = nullptr;
+  float* h_poses = nullptr;
+  rst_stats* h_stats = nullptr;
+
+  int n_pairs_last = 0;
+  int64_t launches = 0;
+  std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+#define RST_CUDA(ctx, expr)                                                              \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                   \
+      return RST_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+static int fail(rst_ctx* c, int code, const char* msg) {
+  if (c) c->err = msg;
+  return code;
+}
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+/* pyramid level geometry — identical expressions to the CPU specification */
+static void level_geom(const rst_intrinsics& K, int w, int h, int level, LevelGeom* g) {
+  g->w = w; g->h = h; g->fx = K.fx; g->fy = K.fy; g->cx = K.cx; g->cy = K.cy;
+  for (int l = 0; l < level; ++l) {
+    g->w /= 2; g->h /= 2;
+    g->fx = g->fx * 0.5f; g->fy = g->fy * 0.5f;
+    g->cx = (g->cx + 0.5f) * 0.5f - 0.5f;
+    g->cy = (g->cy + 0.5f) * 0.5f - 0.5f;
+  }
+  g->ifx = 1.0f / g->fx;
+  g->ify = 1.0f / g->fy;
+}
+
+extern "C" {
+
+int32_t rst_abi_version(void) { return RST_ABI_VERSION; }
+
+void rst_params_default(rst_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->num_levels = 3;
+  p->iters[0] = 10; p->iters[1] = 5; p->iters[2] = 4; p->iters[3] = 0;
+  p->depth_scale = 0.001f;
+  p->z_min = 0.1f; p->z_max = 10.0f;
+  p->dist_max = 0.2f;
+  p->normal_cos_min = -2.0f;
+  p->normal_depth_tol = 0.05f;
+  p->pyr_depth_tol = 100;
+  p->robust_kind = RST_ROBUST_NONE;
+  p->robust_scale = 0.02f;
+  p->min_count = 16;
+  p->damping = 0.0f;
+  p->photo_weight = 0.0f;
+}
+
+const char* rst_last_error(const rst_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+const char* rst_last_create_error(void) { return g_create_err.c_str(); }
+int64_t rst_launch_count(const rst_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void rst_ctx_destroy(rst_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int l = 0; l < RST_MAX_LEVELS; ++l) { cudaFree(c->d_depth[l]); cudaFree(c->d_geom[l]); }
+  cudaFree(c->d_pairs); cudaFree(c->d_poses_in); cudaFree(c->d_master); cudaFree(c->d_pose_f32);
+  cudaFree(c->d_poses_cm); cudaFree(c->d_stats); cudaFree(c->d_tickets); cudaFree(c->d_partials);
+  cudaFree(c->d_idx);
+  cudaFreeHost(c->h_pairs); cudaFreeHost(c->h_poses); cudaFreeHost(c->h_stats);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int32_t rst_ctx_create(int32_t device, int32_t max_w, int32_t max_h, int32_t max_frames,
+                       int32_t max_pairs, void* stream, rst_ctx** out) {
+  g_create_err.clear();
+  if (!out) { g_create_err = "out_ctx is null"; return RST_ERR_INVALID_ARG; }
+  *out = nullptr;
+  if (max_w < 16 || max_h < 16 || max_frames < 2 || max_pairs < 1 || max_w > 16384 || max_h > 16384) {
+    g_create_err = "bad capacity (need max_w,max_h >= 16, max_frames >= 2, max_pairs >= 1)";
+    return RST_ERR_INVALID_ARG;
+  }
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= 0) {
+    g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e);
+    return RST_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n_dev) { g_create_err = "device id out of range"; return RST_ERR_NO_DEVICE; }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    g_create_err = cudaGetErrorString(e);
+    return RST_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    g_create_err = "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                   "; this library carries sm_100a code only";
+    return RST_ERR_ARCH;
+  }
+  rst_ctx* c = new (std::nothrow) rst_ctx();
+  if (!c) { g_create_err = "out of host memory"; return RST_ERR_INVALID_ARG; }
+  c->device = device; c->max_w = max_w; c->max_h = max_h; c->max_frames = max_frames; c->max_pairs = max_pairs;
+#define CREATE_TRY(expr)                                                              \
+  do {                                                                                \
+    cudaError_t e2_ = (expr);                                                         \
+    if (e2_ != cudaSuccess) {                                                         \
+      g_create_err = std::string(#expr) + ": " + cudaGetErrorString(e2_);             \
+      rst_ctx_destroy(c);                                                             \
+      return RST_ERR_CUDA;                                                            \
+    }                                                                                 \
+  } while (0)
+  CREATE_TRY(cudaSetDevice(device));
+  if (stream) { c->stream = (cudaStream_t)stream; }
+  else { CREATE_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  int w = max_w, h = max_h;
+  for (int l = 0; l < RST_MAX_LEVELS; ++l) {
+    const size_t px = (size_t)round_up(w, 8) * h;
+    c->depth_bytes[l] = px * sizeof(uint16_t) * max_frames;
+    CREATE_TRY(cudaMalloc(&c->d_depth[l], c->depth_bytes[l]));
+    CREATE_TRY(cudaMalloc(&c->d_geom[l], (size_t)w * h * sizeof(float4) * max_frames));
+    w /= 2; h /= 2;
+    if (w < 1) w = 1;
+    if (h < 1) h = 1;
+  }
+  const int np = max_pairs + 1;
+  const int cpr = (max_w + kChunkPx - 1) / kChunkPx;
+  c->max_blocks = (cpr * max_h + kChunksPerBlock - 1) / kChunksPerBlock;
+  CREATE_TRY(cudaMalloc(&c->d_pairs, sizeof(int2) * np));
+  CREATE_TRY(cudaMalloc(&c->d_poses_in, sizeof(float) * 16 * np));
+  CREATE_TRY(cudaMalloc(&c->d_master, sizeof(double) * 12 * np));
+  CREATE_TRY(cudaMalloc(&c->d_pose_f32, sizeof(float) * 12 * np));
+  CREATE_TRY(cudaMalloc(&c->d_poses_cm, sizeof(float) * 16 * np));
+  CREATE_TRY(cudaMalloc(&c->d_stats, sizeof(rst_stats) * np));
+  CREATE_TRY(cudaMalloc(&c->d_tickets, sizeof(uint32_t) * np));
+  CREATE_TRY(cudaMemset(c->d_tickets, 0, sizeof(uint32_t) * np));
+  CREATE_TRY(cudaMalloc(&c->d_partials, sizeof(float) * kAccPad * (size_t)c->max_blocks * np));
+  CREATE_TRY(cudaMallocHost(&c->h_pairs, sizeof(int2) * np));
+  CREATE_TRY(cudaMallocHost(&c->h_poses, sizeof(float) * 16 * np));
+  CREATE_TRY(cudaMallocHost(&c->h_stats, sizeof(rst_stats) * np));
+#undef CREATE_TRY
+  *out = c;
+  return RST_OK;
+}
+
+int32_t rst_begin(rst_ctx* c, int32_t width, int32_t height, const rst_intrinsics* intr,
+                  const rst_params* params) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  if (!intr || !params) return fail(c, RST_ERR_INVALID_ARG, "intr/params is null");
+  if (width < 16 || height < 16) return fail(c, RST_ERR_INVALID_ARG, "frame smaller than 16x16");
+  if (width > c->max_w || height > c->max_h) return fail(c, RST_ERR_CAPACITY, "frame larger than the context capacity");
+  const rst_params& P = *params;
+  if (P.num_levels < 1 || P.num_levels > RST_MAX_LEVELS) return fail(c, RST_ERR_INVALID_ARG, "num_levels out of range");
+  for (int l = 0; l < P.num_levels; ++l)
+    if (P.iters[l] < 0 || P.iters[l] > 10000) return fail(c, RST_ERR_INVALID_ARG, "iters out of range");
+  if (!(P.depth_scale > 0.f) || !(P.dist_max > 0.f) || !(P.z_max > P.z_min) || !(intr->fx > 0.f) || !(intr->fy > 0.f))
+    return fail(c, RST_ERR_INVALID_ARG, "depth_scale, dist_max, z range and focal lengths must be positive");
+  if (P.robust_kind < 0 || P.robust_kind > 2) return fail(c, RST_ERR_INVALID_ARG, "unknown robust_kind");
+  if (P.robust_kind != RST_ROBUST_NONE && !(P.robust_scale > 0.f)) return fail(c, RST_ERR_INVALID_ARG, "robust_scale must be positive");
+  if ((width >> (P.num_levels - 1)) < 8 || (height >> (P.num_levels - 1)) < 8)
+    return fail(c, RST_ERR_INVALID_ARG, "coarsest pyramid level smaller than 8x8");
+  RST_CUDA(c, cudaSetDevice(c->device));
+  const bool same = c->begun && c->w == width && c->h == height;
+  c->w = width; c->h = height; c->K = *intr; c->P = P; c->num_levels = P.num_levels;
+  for (int l = 0; l < P.num_levels; ++l) {
+    level_geom(*intr, width, height, l, &c->geom[l]);
+    c->pitch[l] = round_up(c->geom[l].w, 8);
+    c->dframe[l] = (int64_t)c->pitch[l] * c->geom[l].h;
+    c->gframe[l] = (int64_t)c->geom[l].w * c->geom[l].h;
+    c->chunks_per_row[l] = (c->geom[l].w + kChunkPx - 1) / kChunkPx;
+    c->n_chunks[l] = c->chunks_per_row[l] * c->geom[l].h;
+    c->blocks_per_pair[l] = (c->n_chunks[l] + kChunksPerBlock - 1) / kChunksPerBlock;
+  }
+  if (!same || c->store_dirty) {
+    // row padding (columns >= w) must read as invalid depth
+    for (int l = 0; l < RST_MAX_LEVELS; ++l) RST_CUDA(c, cudaMemsetAsync(c->d_depth[l], 0, c->depth_bytes[l], c->stream));
+    c->store_dirty = false;
+  }
+  c->ext0 = false; c->ext_depth0 = nullptr;
+  c->begun = true;
+  c->err.clear();
+  return RST_OK;
+}
+
+int32_t rst_upload_frames(rst_ctx* c, const rst_frame* frames, int32_t n, int32_t first_slot) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  if (!c->begun) return fail(c, RST_ERR_INVALID_ARG, "rst_begin has not been called");
+  if (!frames || n < 0 || first_slot < 0) return fail(c, RST_ERR_INVALID_ARG, "bad frames/n/first_slot");
+  if (first_slot + n > c->max_frames) return fail(c, RST_ERR_CAPACITY, "more frames than the context holds");
+  if (c->ext0) return fail(c, RST_ERR_INVALID_ARG, "level 0 is bound to device memory; call rst_begin first");
+  RST_CUDA(c, cudaSetDevice(c->device));
+  for (int i = 0; i < n; ++i) {
+    const rst_frame& f = frames[i];
+    if (!f.depth) return fail(c, RST_ERR_INVALID_ARG, "frame.depth is null");
+    if (f.width != c->w || f.height != c->h) return fail(c, RST_ERR_INVALID_ARG, "frame size differs from rst_begin");
+    if (f.depth_stride_bytes < c->w * 2 || (f.depth_stride_bytes & 1)) return fail(c, RST_ERR_INVALID_ARG, "bad depth stride");
+  }
+  const size_t dpitch = (size_t)c->pitch[0] * 2;
+  int i = 0;
+  while (i < n) {
+    // merge frames that lie back to back in host memory into one copy
+    int j = i;
+    const size_t stride = (size_t)frames[i].depth_stride_bytes;
+    while (j + 1 < n && (size_t)frames[j + 1].depth_stride_bytes == stride &&
+           (const uint8_t*)frames[j + 1].depth == (const uint8_t*)frames[j].depth + stride * c->h)
+      ++j;
+    const int cnt = j - i + 1;
+    uint16_t* dst = c->d_depth[0] + (int64_t)(first_slot + i) * c->dframe[0];
+    RST_CUDA(c, cudaMemcpy2DAsync(dst, dpitch, frames[i].depth, stride, (size_t)c->w * 2, (size_t)c->h * cnt,
+                                  cudaMemcpyHostToDevice, c->stream));
+    i = j + 1;
+  }
+  return RST_OK;
+}
+
+int32_t rst_set_frames_device(rst_ctx* c, const uint16_t* d_depth, int32_t n, int32_t row_stride_px,
+                              int64_t frame_stride_px, int32_t first_slot) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  if (!c->begun) return fail(c, RST_ERR_INVALID_ARG, "rst_begin has not been called");
+  if (!d_depth || n < 1 || first_slot < 0) return fail(c, RST_ERR_INVALID_ARG, "bad d_depth/n/first_slot");
+  if (first_slot + n > c->max_frames) return fail(c, RST_ERR_CAPACITY, "more frames than the context holds");
+  if (row_stride_px < c->w || frame_stride_px < (int64_t)row_stride_px * c->h)
+    return fail(c, RST_ERR_INVALID_ARG, "strides smaller than the frame");
+  if (((uintptr_t)d_depth & 15) || (row_stride_px & 7) || (frame_stride_px & 7))
+    return fail(c, RST_ERR_ALIGNMENT, "device depth must be 16-byte aligned with row/frame strides multiples of 8 pixels");
+  c->ext0 = true;
+  c->ext_depth0 = d_depth - (int64_t)first_slot * frame_stride_px;
+  c->ext_pitch0 = row_stride_px;
+  c->ext_frame0 = frame_stride_px;
+  return RST_OK;
+}
+
+static LevelStore level_store(const rst_ctx* c, int l) {
+  LevelStore s;
+  if (l == 0 && c->ext0) { s.depth = c->ext_depth0; s.depth_pitch = c->ext_pitch0; s.depth_frame = c->ext_frame0; }
+  else { s.depth = c->d_depth[l]; s.depth_pitch = c->pitch[l]; s.depth_frame = c->dframe[l]; }
+  s.geom = c->d_geom[l];
+  s.geom_frame = c->gframe[l];
+  return s;
+}
+
+static int32_t preprocess_impl(rst_ctx* c, int first_slot, int n, bool write_geom) {
+  for (int l = 0; l < c->num_levels; ++l) {
+    const bool has_next = l + 1 < c->num_levels;
+    if (!write_geom && !has_next) break;
+    PreArgs a{};
+    a.g = c->geom[l];
+    a.cur = level_store(c, l);
+    if (!write_geom) a.cur.geom = nullptr;
+    if (has_next) {
+      a.next_depth = c->d_depth[l + 1]; a.next_pitch = c->pitch[l + 1]; a.next_frame = c->dframe[l + 1];
+      a.next_w = c->geom[l + 1].w; a.next_h = c->geom[l + 1].h;
+    }
+    a.first_slot = first_slot;
+    a.depth_scale = c->P.depth_scale; a.z_min = c->P.z_min; a.z_max = c->P.z_max;
+    a.normal_depth_tol = c->P.normal_depth_tol; a.pyr_tol = c->P.pyr_depth_tol;
+    RST_CUDA(c, launch_preprocess(a, n, c->stream));
+    c->launches += 1;
+  }
+  return RST_OK;
+}
+
+int32_t rst_preprocess(rst_ctx* c, int32_t first_slot, int32_t n) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  if (!c->begun) return fail(c, RST_ERR_INVALID_ARG, "rst_begin has not been called");
+  if (first_slot < 0 || n < 0 || first_slot + n > c->max_frames) return fail(c, RST_ERR_CAPACITY, "slot range out of capacity");
+  RST_CUDA(c, cudaSetDevice(c->device));
+  return preprocess_impl(c, first_slot, n, true);
+}
+
+static void fill_icp_args(const rst_ctx* c, int l, IcpArgs* a) {
+  a->g = c->geom[l];
+  a->lv = level_store(c, l);
+  a->pairs = c->d_pairs;
+  a->pair_offset = 0;
+  a->pose_f32 = c->d_pose_f32;
+  a->partials = c->d_partials;
+  a->tickets = c->d_tickets;
+  a->max_blocks = c->max_blocks;
+  a->blocks_per_pair = c->blocks_per_pair[l];
+  a->chunks_per_row = c->chunks_per_row[l];
+  a->n_chunks = c->n_chunks[l];
+  a->depth_scale = c->P.depth_scale; a->z_min = c->P.z_min; a->z_max = c->P.z_max;
+  a->dmax2 = c->P.dist_max * c->P.dist_max;
+  a->ncos_min = c->P.normal_cos_min;
+  a->robust_scale = c->P.robust_scale;
+  a->pose_master = c->d_master;
+  a->pose_f32_out = c->d_pose_f32;
+  a->poses_cm = c->d_poses_cm;
+  a->stats = c->d_stats;
+  a->min_count = c->P.min_count;
+  a->damping = c->P.damping;
+  a->update_pose = 1;
+  a->idx_out = nullptr;
+}
+
+int32_t rst_align_slots(rst_ctx* c, const int32_t* src_slots, const int32_t* dst_slots, int32_t n_pairs,
+                        float* poses_inout, rst_stats* stats_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  if (!c->begun) return fail(c, RST_ERR_INVALID_ARG, "rst_begin has not been called");
+  if (!src_slots || !dst_slots || n_pairs < 0) return fail(c, RST_ERR_INVALID_ARG, "bad slot arrays / n_pairs");
+  if (n_pairs > c->max_pairs) return fail(c, RST_ERR_CAPACITY, "more pairs than the context holds");
+  c->n_pairs_last = n_pairs;
+  if (n_pairs == 0) return RST_OK;
+  RST_CUDA(c, cudaSetDevice(c->device));
+  for (int i = 0; i < n_pairs; ++i) {
+    if (src_slots[i] < 0 || src_slots[i] >= c->max_frames || dst_slots[i] < 0 || dst_slots[i] >= c->max_frames)
+      return fail(c, RST_ERR_INVALID_ARG, "slot index out of range");
+    c->h_pairs[i] = make_int2(src_slots[i], dst_slots[i]);
+  }
+  if (poses_inout) {
+    std::memcpy(c->h_poses, poses_inout, sizeof(float) * 16 * n_pairs);
+  } else {
+    for (int i = 0; i < n_pairs; ++i)
+      for (int k = 0; k < 16; ++k) c->h_poses[16 * i + k] = (k % 5 == 0) ? 1.f : 0.f;
+  }
+  RST_CUDA(c, cudaMemcpyAsync(c->d_pairs, c->h_pairs, sizeof(int2) * n_pairs, cudaMemcpyHostToDevice, c->stream));
+  RST_CUDA(c, cudaMemcpyAsync(c->d_poses_in, c->h_poses, sizeof(float) * 16 * n_pairs, cudaMemcpyHostToDevice, c->stream));
+  InitArgs ia{c->d_poses_in, c->d_master, c->d_pose_f32, c->d_poses_cm, c->d_stats, c->d_tickets, n_pairs};
+  RST_CUDA(c, launch_init_pairs(ia, c->stream));
+  c->launches += 1;
+  const bool ngate = c->P.normal_cos_min > -1.0f;
+  for (int l = c->num_levels - 1; l >= 0; --l) {
+    IcpArgs a{};
+    fill_icp_args(c, l, &a);
+    for (int it = 0; it < c->P.iters[l]; ++it) {
+      for (int off = 0; off < n_pairs; off += 65535) {
+        a.pair_offset = off;
+        const int cnt = n_pairs - off < 65535 ? n_pairs - off : 65535;
+        RST_CUDA(c, launch_icp_iter(a, cnt, c->P.robust_kind, ngate, false, c->stream));
+        c->launches += 1;
+      }
+    }
+  }
+  if (poses_inout || stats_out) {
+    if (poses_inout)
+      RST_CUDA(c, cudaMemcpyAsync(c->h_poses, c->d_poses_cm, sizeof(float) * 16 * n_pairs, cudaMemcpyDeviceToHost, c->stream));
+    if (stats_out)
+      RST_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(rst_stats) * n_pairs, cudaMemcpyDeviceToHost, c->stream));
+    RST_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (poses_inout) std::memcpy(poses_inout, c->h_poses, sizeof(float) * 16 * n_pairs);
+    if (stats_out) std::memcpy(stats_out, c->h_stats, sizeof(rst_stats) * n_pairs);
+  }
+  return RST_OK;
+}
+
+int32_t rst_device_results(rst_ctx* c, const float** d_poses, const rst_stats** d_stats) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  if (d_poses) *d_poses = c->d_poses_cm;
+  if (d_stats) *d_stats = c->d_stats;
+  return RST_OK;
+}
+
+int32_t rst_sync(rst_ctx* c) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  RST_CUDA(c, cudaSetDevice(c->device));
+  RST_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RST_OK;
+}
+
+static int32_t check_frames(rst_ctx* c, const rst_frame* f, int n) {
+  for (int i = 0; i < n; ++i)
+    if (f[i].width != f[0].width || f[i].height != f[0].height) return fail(c, RST_ERR_INVALID_ARG, "frames differ in size");
+  return RST_OK;
+}
+
+int32_t rst_align_pairs(rst_ctx* c, const rst_frame* src, const rst_frame* dst, int32_t n_pairs,
+                        const rst_intrinsics* intr, const rst_params* params, float* poses_inout,
+                        rst_stats* stats_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  if (!src || !dst || n_pairs < 0 || !poses_inout) return fail(c, RST_ERR_INVALID_ARG, "null src/dst/poses or negative n_pairs");
+  if (n_pairs == 0) return RST_OK;
+  if (2 * (int64_t)n_pairs > c->max_frames || n_pairs > c->max_pairs) return fail(c, RST_ERR_CAPACITY, "batch exceeds the context capacity");
+  int32_t rc;
+  if ((rc = check_frames(c, src, n_pairs)) != RST_OK) return rc;
+  if ((rc = rst_begin(c, src[0].width, src[0].height, intr, params)) != RST_OK) return rc;
+  // dst frames in slots [0, n), src frames in [n, 2n)
+  if ((rc = rst_upload_frames(c, dst, n_pairs, 0)) != RST_OK) return rc;
+  if ((rc = rst_upload_frames(c, src, n_pairs, n_pairs)) != RST_OK) return rc;
+  if ((rc = preprocess_impl(c, 0, n_pairs, true)) != RST_OK) return rc;
+  const bool ngate = c->P.normal_cos_min > -1.0f;
+  if ((rc = preprocess_impl(c, n_pairs, n_pairs, ngate)) != RST_OK) return rc;
+  std::vector<int32_t> s(n_pairs), d(n_pairs);
+  for (int i = 0; i < n_pairs; ++i) { d[i] = i; s[i] = n_pairs + i; }
+  return rst_align_slots(c, s.data(), d.data(), n_pairs, poses_inout, stats_out);
+}
+
+int32_t rst_align_sequence(rst_ctx* c, const rst_frame* frames, int32_t n_frames, const rst_intrinsics* intr,
+                           const rst_params* params, float* poses_inout, rst_stats* stats_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  if (!frames || n_frames < 0 || !poses_inout) return fail(c, RST_ERR_INVALID_ARG, "null frames/poses or negative n_frames");
+  if (n_frames < 2) return RST_OK;
+  if (n_frames > c->max_frames || n_frames - 1 > c->max_pairs) return fail(c, RST_ERR_CAPACITY, "sequence exceeds the context capacity");
+  int32_t rc;
+  if ((rc = check_frames(c, frames, n_frames)) != RST_OK) return rc;
+  if ((rc = rst_begin(c, frames[0].width, frames[0].height, intr, params)) != RST_OK) return rc;
+  if ((rc = rst_upload_frames(c, frames, n_frames, 0)) != RST_OK) return rc;
+  if ((rc = preprocess_impl(c, 0, n_frames, true)) != RST_OK) return rc;
+  std::vector<int32_t> s(n_frames - 1), d(n_frames - 1);
+  for (int i = 0; i + 1 < n_frames; ++i) { s[i] = i + 1; d[i] = i; }  // AlignIcp3d(curr, prev): rs_replay_app.cpp:251
+  return rst_align_slots(c, s.data(), d.data(), n_frames - 1, poses_inout, stats_out);
+}
+
+int32_t rst_level_info(const rst_ctx* c, int32_t level, int32_t* width, int32_t* height, int32_t* pitch_px,
+                       rst_intrinsics* intr) {
+  if (!c || !c->begun || level < 0 || level >= c->num_levels) return RST_ERR_INVALID_ARG;
+  if (width) *width = c->geom[level].w;
+  if (height) *height = c->geom[level].h;
+  if (pitch_px) *pitch_px = (level == 0 && c->ext0) ? c->ext_pitch0 : c->pitch[level];
+  if (intr) { intr->fx = c->geom[level].fx; intr->fy = c->geom[level].fy; intr->cx = c->geom[level].cx; intr->cy = c->geom[level].cy; }
+  return RST_OK;
+}
+
+int32_t rst_read_depth(rst_ctx* c, int32_t slot, int32_t level, uint16_t* out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  if (!c->begun || !out || level < 0 || level >= c->num_levels || slot < 0 || slot >= c->max_frames)
+    return fail(c, RST_ERR_INVALID_ARG, "bad slot/level/out");
+  RST_CUDA(c, cudaSetDevice(c->device));
+  const LevelStore s = level_store(c, level);
+  const int w = c->geom[level].w, h = c->geom[level].h;
+  RST_CUDA(c, cudaMemcpy2DAsync(out, (size_t)w * 2, s.depth + (int64_t)slot * s.depth_frame, (size_t)s.depth_pitch * 2,
+                                (size_t)w * 2, h, cudaMemcpyDeviceToHost, c->stream));
+  RST_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RST_OK;
+}
+
+int32_t rst_read_geometry(rst_ctx* c, int32_t slot, int32_t level, float* out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  if (!c->begun || !out || level < 0 || level >= c->num_levels || slot < 0 || slot >= c->max_frames)
+    return fail(c, RST_ERR_INVALID_ARG, "bad slot/level/out");
+  RST_CUDA(c, cudaSetDevice(c->device));
+  const size_t n = (size_t)c->gframe[level];
+  RST_CUDA(c, cudaMemcpyAsync(out, c->d_geom[level] + (int64_t)slot * c->gframe[level], n * sizeof(float4),
+                              cudaMemcpyDeviceToHost, c->stream));
+  RST_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RST_OK;
+}
+
+int32_t rst_evaluate(rst_ctx* c, int32_t src_slot, int32_t dst_slot, int32_t level, const float* pose,
+                     int32_t* idx_out, rst_stats* stats_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  if (!c->begun || !pose || !stats_out || level < 0 || level >= c->num_levels) return fail(c, RST_ERR_INVALID_ARG, "bad level/pose/stats");
+  if (src_slot < 0 || src_slot >= c->max_frames || dst_slot < 0 || dst_slot >= c->max_frames)
+    return fail(c, RST_ERR_INVALID_ARG, "slot index out of range");
+  RST_CUDA(c, cudaSetDevice(c->device));
+  const int sp = c->max_pairs;  // scratch pair
+  c->h_pairs[sp] = make_int2(src_slot, dst_slot);
+  std::memcpy(c->h_poses + 16 * sp, pose, sizeof(float) * 16);
+  RST_CUDA(c, cudaMemcpyAsync(c->d_pairs + sp, c->h_pairs + sp, sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+  RST_CUDA(c, cudaMemcpyAsync(c->d_poses_in + 16 * sp, c->h_poses + 16 * sp, sizeof(float) * 16, cudaMemcpyHostToDevice, c->stream));
+  InitArgs ia{c->d_poses_in + 16 * sp, c->d_master + 12 * sp, c->d_pose_f32 + 12 * sp, c->d_poses_cm + 16 * sp,
+              c->d_stats + sp, c->d_tickets + sp, 1};
+  RST_CUDA(c, launch_init_pairs(ia, c->stream));
+  c->launches += 1;
+  const size_t npx = (size_t)c->gframe[level];
+  if (idx_out && c->idx_bytes < npx * 4) {
+    cudaFree(c->d_idx); c->d_idx = nullptr; c->idx_bytes = 0;
+    RST_CUDA(c, cudaMalloc(&c->d_idx, (size_t)c->max_w * c->max_h * 4));
+    c->idx_bytes = (size_t)c->max_w * c->max_h * 4;
+  }
+  IcpArgs a{};
+  fill_icp_args(c, level, &a);
+  a.pair_offset = sp;
+  a.update_pose = 0;
+  a.idx_out = idx_out ? c->d_idx : nullptr;
+  RST_CUDA(c, launch_icp_iter(a, 1, c->P.robust_kind, c->P.normal_cos_min > -1.0f, idx_out != nullptr, c->stream));
+  c->launches += 1;
+  RST_CUDA(c, cudaMemcpyAsync(c->h_stats + sp, c->d_stats + sp, sizeof(rst_stats), cudaMemcpyDeviceToHost, c->stream));
+  if (idx_out) RST_CUDA(c, cudaMemcpyAsync(idx_out, c->d_idx, npx * 4, cudaMemcpyDeviceToHost, c->stream));
+  RST_CUDA(c, cudaStreamSynchronize(c->stream));
+  *stats_out = c->h_stats[sp];
+  return RST_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+/*
+ * rst_kernels.cuh — argument blocks and launchers of the sm_100a alignment kernels.
+ *
+ *   K1+K2+K6  k_preprocess : uint16 depth tile (+1 px halo) -> shared memory via 128-bit
+ *                            loads; back-projection, normals -> geometry map float4
+ *                            {nx,ny,nz,z}; 2x2 integer pooling -> next pyramid level.
+ *   K3+K4+K5  k_icp_iter   : projective association + point-to-plane residual/Jacobian,
+ *                            29 sums per thread -> warp shuffle tree -> block tree ->
+ *                            per-block partials -> last block of each pair (ticket) sums
+ *                            them in fixed order in fp64, solves the 6x6 system by
+ *                            Cholesky and updates the pose on the device.
+ *   k_init_pairs           : pose upload -> fp64 master pose, state reset.
+ *
+ * Nearest reference counterparts: align_icp.cpp:101-151 (correspondence loop,
+ * covariance accumulation, closed-form solve), rs_driver.cpp:201-202 (back-projection),
+ * point_cloud_utils.cpp:176-216 (normals + orientation).
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rst_align.h"
+
+namespace rst {
+
+constexpr int kAcc = 29;          // 21 (A upper) + 6 (b) + sum w r^2 + count
+constexpr int kAccPad = 32;       // partial row stride (floats)
+constexpr int kIcpThreads = 256;
+constexpr int kChunkPx = 64;      // pixels one warp covers per step (2 per lane)
+constexpr int kChunksPerWarp = 4; // steps per warp -> 8 pixels per thread
+constexpr int kChunksPerBlock = (kIcpThreads / 32) * kChunksPerWarp;  // 32 -> 2048 px
+constexpr int kTileW = 64, kTileH = 32;  // preprocess tile
+
+struct LevelGeom {
+  int32_t w, h;
+  float fx, fy, cx, cy, ifx, ify;
+};
+
+/* one pyramid level of the frame store */
+struct LevelStore {
+  const uint16_t* depth;     // slot 0, row 0
+  int32_t depth_pitch;       // pixels between rows
+  int64_t depth_frame;       // pixels between frames
+  float4* geom;              // dense w*h per frame
+  int64_t geom_frame;        // float4 between frames
+};
+
+struct PreArgs {
+  LevelGeom g;
+  LevelStore cur;
+  uint16_t* next_depth;      // next level (nullable)
+  int32_t next_pitch;
+  int64_t next_frame;
+  int32_t next_w, next_h;
+  int32_t first_slot;
+  float depth_scale, z_min, z_max, normal_depth_tol;
+  int32_t pyr_tol;
+};
+
+struct IcpArgs {
+  LevelGeom g;
+  LevelStore lv;
+  const int2* pairs;          // (src slot, dst slot)
+  int32_t pair_offset;        // index of the first pair this launch handles
+  const float* pose_f32;      // 12 per pair: row-major R, t
+  float* partials;            // [pair][max_blocks][kAccPad]
+  uint32_t* tickets;          // [pair]
+  int32_t max_blocks;
+  int32_t blocks_per_pair, chunks_per_row, n_chunks;
+  float depth_scale, z_min, z_max, dmax2, ncos_min, robust_scale;
+  /* finalize */
+  double* pose_master;        // 12 per pair
+  float* pose_f32_out;        // == pose_f32 (written by the last block)
+  float* poses_cm;            // 16 per pair, column-major 4x4 result
+  rst_stats* stats;
+  int32_t min_count;
+  float damping;
+  int32_t update_pose;        // 0: evaluate only
+  int32_t* idx_out;           // WRITE_IDX: [pair-local][h*w]
+};
+
+struct InitArgs {
+  const float* poses_cm_in;   // 16 per pair
+  double* pose_master;
+  float* pose_f32;
+  float* poses_cm;
+  rst_stats* stats;
+  uint32_t* tickets;
+  int32_t n_pairs;
+};
+
+cudaError_t launch_preprocess(const PreArgs& a, int n_frames, cudaStream_t s);
+cudaError_t launch_icp_iter(const IcpArgs& a, int n_pairs, int robust_kind, bool normal_gate,
+                            bool write_idx, cudaStream_t s);
+cudaError_t launch_init_pairs(const InitArgs& a, cudaStream_t s);
+
+}  // namespace rst

@@ -1,0 +1,263 @@
+"""GPU parity: the CUDA path (through the C ABI) against Oracle-N on the same seeded inputs.
+
+Bars (BASELINE.json north_star): pyramid / geometry map / association indices bit-exact;
+normal equations within 1e-4 relative; poses within 1e-4 m and 1e-4 rad.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from realsensetracker_b200 import Aligner, default_params, synth
+from realsensetracker_b200 import _native as N
+
+pytestmark = pytest.mark.gpu
+
+TOL_M = 1e-4    # metres
+TOL_RAD = 1e-4  # radians
+TOL_NE = 1e-4   # relative, normal equations
+
+
+def oparams(**kw):
+    return O.default_params(**kw)
+
+
+def both_params(**kw):
+    return default_params(**kw), O.default_params(**kw)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def oracle_levels(frame, intr, P):
+    lv, d = [], frame
+    for l in range(P.num_levels):
+        L = O.level_info(intr, frame.shape[1], frame.shape[0], l)
+        if l > 0:
+            d = O.pyr_down(d, P.pyr_depth_tol)
+        lv.append((L, d, O.geometry(d, L, P)))
+    return lv
+
+
+@pytest.fixture(scope="module", params=["640", "small"])
+def staged(request, seq640, seq_small):
+    frames, gt, intr = seq640 if request.param == "640" else seq_small
+    n, h, w = frames.shape
+    P, Po = both_params()
+    al = Aligner(w, h, n, n)
+    al.begin(w, h, intr, P)
+    al.upload(frames)
+    al.preprocess(0, n)
+    yield al, frames, gt, intr, P, Po
+    al.close()
+
+
+def test_pyramid_bit_exact(staged):
+    al, frames, gt, intr, P, Po = staged
+    for slot in range(2):
+        d = frames[slot]
+        assert np.array_equal(al.read_depth(slot, 0), d)
+        for l in range(1, P.num_levels):
+            d = O.pyr_down(d, Po.pyr_depth_tol)
+            got = al.read_depth(slot, l)
+            assert got.shape == d.shape
+            assert np.array_equal(got, d), f"pyramid level {l} differs"
+
+
+def test_level_intrinsics_match(staged):
+    al, frames, gt, intr, P, Po = staged
+    for l in range(P.num_levels):
+        w, h, pitch, K = al.level_info(l)
+        L = O.level_info(intr, frames.shape[2], frames.shape[1], l)
+        assert (w, h) == (L.w, L.h)
+        assert np.array_equal(np.float32(K), np.float32([L.fx, L.fy, L.cx, L.cy]))
+        assert pitch % 8 == 0 and pitch >= w
+
+
+def test_geometry_map_bit_exact(staged):
+    al, frames, gt, intr, P, Po = staged
+    for slot in range(2):
+        for l, (L, d, G) in enumerate(oracle_levels(frames[slot], intr, Po)):
+            got = al.read_geometry(slot, l)
+            assert got.shape == G.shape
+            valid = G[..., 3] > 0
+            assert valid.mean() > 0.5
+            assert np.array_equal(got.view(np.uint32), G.view(np.uint32)), f"geometry level {l} differs"
+
+
+@pytest.mark.parametrize("pose_kind", ["identity", "gt", "perturbed"])
+def test_association_bit_exact_and_normal_equations(staged, pose_kind):
+    al, frames, gt, intr, P, Po = staged
+    T = {"identity": np.eye(4), "gt": gt[0],
+         "perturbed": gt[0] @ synth.make_pose(synth.rotvec_to_R([0.01, -0.02, 0.015]), [0.02, -0.01, 0.03])}[pose_kind]
+    T = np.asarray(T, dtype=np.float32).astype(np.float64)
+    src_lv = oracle_levels(frames[1], intr, Po)
+    dst_lv = oracle_levels(frames[0], intr, Po)
+    for l in range(P.num_levels):
+        L, ds, _ = src_lv[l]
+        idx_o, st_o = O.evaluate(ds, None, dst_lv[l][2], L, Po, T)
+        idx_g, st_g = al.evaluate(1, 0, l, T)
+        assert np.array_equal(idx_g, idx_o), f"association differs at level {l}: {(idx_g != idx_o).sum()} px"
+        assert st_g.count == st_o.count == int((idx_o >= 0).sum())
+        assert st_o.count > 1000
+        assert rel_err(st_g.A[:], st_o.A[:]) < TOL_NE
+        assert rel_err(st_g.b[:], st_o.b[:]) < TOL_NE * max(1.0, np.max(np.abs(st_o.A[:])) / max(np.max(np.abs(st_o.b[:])), 1e-30) * 1e-3)
+        assert abs(st_g.sum_wr2 - st_o.sum_wr2) <= TOL_NE * st_o.sum_wr2 + 1e-12
+
+
+@pytest.mark.parametrize("kind,scale", [(N.RST_ROBUST_HUBER, 0.002), (N.RST_ROBUST_GEMAN_MCCLURE, 1e-4)])
+def test_robust_weights_and_normal_gate(seq_small, kind, scale):
+    frames, gt, intr = seq_small
+    n, h, w = frames.shape
+    kw = dict(robust_kind=kind, robust_scale=scale, normal_cos_min=0.9)
+    P, Po = both_params(**kw)
+    al = Aligner(w, h, n, n)
+    try:
+        al.begin(w, h, intr, P)
+        al.upload(frames)
+        al.preprocess(0, n)
+        T = np.eye(4)
+        src_lv, dst_lv = oracle_levels(frames[2], intr, Po), oracle_levels(frames[1], intr, Po)
+        for l in range(P.num_levels):
+            L, ds, Gs = src_lv[l]
+            idx_o, st_o = O.evaluate(ds, Gs, dst_lv[l][2], L, Po, T)
+            idx_g, st_g = al.evaluate(2, 1, l, T)
+            assert np.array_equal(idx_g, idx_o)
+            assert rel_err(st_g.A[:], st_o.A[:]) < TOL_NE
+            assert abs(st_g.sum_wr2 - st_o.sum_wr2) <= TOL_NE * st_o.sum_wr2
+    finally:
+        al.close()
+
+
+def _check_pose(Tg, To, gt=None, gt_tol=(2e-3, 2e-3)):
+    dt, dr = synth.pose_error(Tg, To)
+    assert dt < TOL_M and dr < TOL_RAD, f"GPU vs oracle pose: {dt} m, {dr} rad"
+    if gt is not None:
+        et, er = synth.pose_error(Tg, gt)
+        assert et < gt_tol[0] and er < gt_tol[1], f"GPU vs ground truth: {et} m, {er} rad"
+
+
+def test_pose_parity_pairs_640(seq640):
+    frames, gt, intr = seq640
+    P, Po = both_params()
+    al = Aligner(640, 480, 8, 4)
+    try:
+        Tg, st = al.align_pairs(frames[1:4], frames[0:3], intr, P)
+        for i in range(3):
+            To, so = O.align_pair(frames[i + 1], frames[i], intr, Po)
+            assert st[i].status == 0 and so.status == 0
+            assert st[i].iterations == so.iterations == 19
+            _check_pose(Tg[i], To, gt[i])
+            assert st[i].count == so.count or abs(st[i].count - so.count) <= 4
+            assert rel_err(st[i].A[:], so.A[:]) < TOL_NE
+            assert abs(st[i].rmse - so.rmse) < 1e-6
+    finally:
+        al.close()
+
+
+def test_sequence_equals_pairs_and_is_deterministic(seq640):
+    frames, gt, intr = seq640
+    P, _ = both_params()
+    al = Aligner(640, 480, 10, 5)
+    try:
+        Ts, _ = al.align_sequence(frames, intr, P)
+        Ts2, _ = al.align_sequence(frames, intr, P)
+        Tp, _ = al.align_pairs(frames[1:], frames[:-1], intr, P)
+        T1, _ = al.align_pairs(frames[2:3], frames[1:2], intr, P)   # batch of one
+        assert np.array_equal(Ts, Ts2), "two runs differ bitwise"
+        assert np.array_equal(Ts, Tp), "sequence API and pairs API differ bitwise"
+        assert np.array_equal(T1[0], Ts[1]), "result depends on the batch size"
+    finally:
+        al.close()
+
+
+def test_initial_pose_is_used_and_large_motion(seq640):
+    """KAT from the reference's disabled self-test (rs_align_app.cpp:257-263): known rotation
+    R_x(0.1) R_y(-0.2) R_z(0.25), scaled to a trackable magnitude, recovered from an initial guess."""
+    frames, gt, intr = seq640
+    scene = synth.Scene(0)
+    Rk = synth.rot_xyz(0.1 * 0.3, -0.2 * 0.3, 0.25 * 0.3)
+    T_src = synth.make_pose(Rk, [0.03, -0.02, 0.04])
+    src = scene.render(T_src, 640, 480)
+    dst = scene.render(np.eye(4), 640, 480)
+    T_gt = synth.relative_pose(np.eye(4), T_src)
+    kw = dict(iters=[10, 10, 10], dist_max=0.5)
+    P, Po = both_params(**kw)
+    T0 = T_gt @ synth.make_pose(synth.rotvec_to_R([0.01, 0.01, -0.01]), [0.01, -0.01, 0.01])
+    al = Aligner(640, 480, 2, 1)
+    try:
+        for init in (None, T0):
+            Tg, st = al.align_pairs(src[None], dst[None], intr, P, T0=init)
+            To, so = O.align_pair(src, dst, intr, Po, T0=init)
+            assert st[0].status == 0
+            _check_pose(Tg[0], To, T_gt, gt_tol=(3e-3, 2e-3))
+    finally:
+        al.close()
+
+
+def test_invalid_depth_and_failure_status(seq_small):
+    frames, gt, intr = seq_small
+    n, h, w = frames.shape
+    P, Po = both_params()
+    al = Aligner(w, h, 4, 2)
+    try:
+        # 30 % invalid (Bernoulli + blocks) still aligns and matches the oracle
+        rng = np.random.default_rng(1)
+        src, dst = frames[1].copy(), frames[0].copy()
+        for f in (src, dst):
+            f[rng.random(f.shape) < 0.2] = 0
+            for _ in range(12):
+                y, x = rng.integers(0, h - 16), rng.integers(0, w - 16)
+                f[y:y + 16, x:x + 16] = 0
+        Tg, st = al.align_pairs(src[None], dst[None], intr, P)
+        To, so = O.align_pair(src, dst, intr, Po)
+        assert st[0].status == 0
+        _check_pose(Tg[0], To, gt[0], gt_tol=(5e-3, 5e-3))
+        # all-invalid source: too few associations -> failure status, pose unchanged (align_icp.cpp:77-79)
+        zero = np.zeros_like(src)
+        Tg, st = al.align_pairs(zero[None], dst[None], intr, P)
+        To, so = O.align_pair(zero, dst, intr, Po)
+        assert st[0].status == so.status == N.RST_STATUS_TOO_FEW
+        assert np.array_equal(Tg[0], np.eye(4))
+        assert st[0].count == 0
+    finally:
+        al.close()
+
+
+def test_device_resident_frames_match_host_path(seq640):
+    import torch
+    frames, gt, intr = seq640
+    P, _ = both_params()
+    n = frames.shape[0]
+    al = Aligner(640, 480, n, n)
+    try:
+        Th, _ = al.align_sequence(frames, intr, P)
+        d = torch.from_numpy(frames.astype(np.int16)).cuda()
+        al.begin(640, 480, intr, P)
+        al.set_frames_device(d.data_ptr(), n, 640, 640 * 480)
+        al.preprocess(0, n)
+        Td, st = al.align_slots(np.arange(1, n), np.arange(0, n - 1))
+        assert np.array_equal(Th, Td)
+        with pytest.raises(Exception):
+            al.set_frames_device(d.data_ptr() + 2, n, 640, 640 * 480)
+    finally:
+        al.close()
+
+
+def test_capacity_and_argument_errors():
+    al = Aligner(64, 48, 2, 1)
+    try:
+        big = np.zeros((1, 96, 128), dtype=np.uint16)
+        with pytest.raises(Exception) as e:
+            al.align_pairs(big, big, (100, 100, 64, 48))
+        assert "CAPACITY" in str(e.value)
+        ok = np.zeros((3, 48, 64), dtype=np.uint16)
+        with pytest.raises(Exception) as e:
+            al.align_pairs(ok, ok, (50, 50, 32, 24))
+        assert "CAPACITY" in str(e.value)
+        with pytest.raises(Exception) as e:
+            al.align_pairs(ok[:1], ok[:1], (50, 50, 32, 24), default_params(num_levels=9))
+        assert "INVALID_ARG" in str(e.value)
+    finally:
+        al.close()
