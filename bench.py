@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — frame-to-frame ICP throughput on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the alignment hot path over one batch of synthetic input: a
+640x480 depth sequence of F frames (F-1 frame-to-frame pairs, identity prior, 3-level
+pyramid, (10,5,4) iterations) per GPU.  Per-GPU work is fixed (weak scaling); pairs are
+independent, so there is no collective on the data path — NCCL only gathers the per-pair
+poses (one all_gather per step).
+
+  value    : pairs/s with the depth frames already resident in HBM
+  e2e      : pairs/s through the public call (rst_align_sequence) with PINNED HOST frames:
+             H2D of all frames and D2H of poses + statistics inside the timed region
+  roofline : level-0 fused ICP kernel, CUDA events around the 10 level-0 launches of each step
+  cpu_baseline : Oracle-R (restatement of the reference's AlignIcp3d path) on the host cores
+
+`--impl reference` times only that CPU path (the reference has no GPU code and cannot be
+built here).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+W, H = 640, 480
+FRAMES = 129                    # 128 pairs per GPU per step
+ITERS = (10, 5, 4)
+SURVEY_BYTES_PER_PX = 36        # src vertex 12 + dst vertex 12 + dst normal 12
+METRIC = "icp_frame_pairs_per_sec_640x480"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the level-0 ICP kernel from the committed ncu capture, if any."""
+    p = ROOT / "profiles" / "icp_l0_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text())
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, uuid: str | None):
+        self.rows, self.proc, self.t = [], None, None
+        cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"]
+        if uuid:
+            cmd += ["-i", uuid]
+        try:
+            self.proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sel = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.05] or [r for (_, r) in self.rows]
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in sel:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: Oracle-R (the reference's own algorithm) on the host cores
+# --------------------------------------------------------------------------------------------
+def cpu_reference_rate(frames: np.ndarray, intr, n_pairs: int, threads: int):
+    """pairs/s of Oracle-R over `n_pairs` consecutive frame pairs with `threads` host threads."""
+    from oracle import oracle as O
+    src = np.ascontiguousarray(frames[1:n_pairs + 1])
+    dst = np.ascontiguousarray(frames[0:n_pairs])
+    t0 = time.perf_counter()
+    ok, T = O.align_depth_pairs(src, dst, intr, voxel=0.05, max_iter=128, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return n_pairs / dt, dt, T, ok
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    from realsensetracker_b200 import synth
+    cores = host_cores()
+    n_pairs = max(cores, 2)                      # one pair per host thread per step
+    intr = synth.intrinsics_for(W, H)
+    frames, gt = synth.render_sequence(n_pairs + 1, W, H, seed=0)
+    for _ in range(args.warmup):
+        cpu_reference_rate(frames, intr, min(n_pairs, cores), cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, _, T, ok = cpu_reference_rate(frames, intr, n_pairs, cores)
+    dt = time.perf_counter() - t0
+    value = n_pairs * args.steps / dt
+    errs = [synth.pose_error(T[i], gt[i]) for i in range(n_pairs)]
+    sample = (f"{n_pairs} consecutive frame pairs of the 640x480 sequence per step, one pair per thread: "
+              "back-project -> RemoveNans -> DownsampleVoxel(0.05) -> AlignIcp3d(128 it, leaf 16); "
+              "g++ -O2 -ffp-contract=off (the reference sets no flags)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "seq640x480_f2f_icp", "frames_per_step": n_pairs + 1, "pairs_per_step": n_pairs,
+                   "algorithm": "reference AlignIcp3d (KD-tree point-to-point, GNC Geman-McClure, Kabsch), CPU"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "pose_err_vs_gt": {"t_m_max": max(e[0] for e in errs), "r_rad_max": max(e[1] for e in errs)},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def run_gpu(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+    from realsensetracker_b200 import Aligner, default_params, synth
+    from realsensetracker_b200 import _native as N
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the alignment path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    intr = synth.intrinsics_for(W, H)
+    P = default_params(num_levels=3, iters=list(ITERS))
+    n_pairs = FRAMES - 1
+
+    # synthetic sequence of this rank, rendered straight into pinned host memory
+    pinned = torch.empty((FRAMES, H, W), dtype=torch.int16, pin_memory=True)
+    frames = pinned.numpy().view(np.uint16)
+    _, gt = synth.render_sequence(FRAMES, W, H, seed=rank, pinned=frames)
+    d_frames = pinned.to(dev)                                   # HBM-resident copy for `value`
+
+    stream = torch.cuda.Stream(device=dev)
+    al = Aligner(W, H, FRAMES, n_pairs, device=local_rank, stream=stream.cuda_stream)
+    src_slots = np.arange(1, FRAMES, dtype=np.int32)
+    dst_slots = np.arange(0, FRAMES - 1, dtype=np.int32)
+    d_poses = torch.empty((n_pairs, 16), dtype=torch.float32, device=dev)
+    d_all = torch.empty((world * n_pairs, 16), dtype=torch.float32, device=dev) if world > 1 else None
+    h_poses = np.tile(np.eye(4, dtype=np.float32).reshape(16), (n_pairs, 1))
+    h_stats = (N.Stats * n_pairs)()
+    K = N.Intrinsics(*intr)
+    fr = __import__("realsensetracker_b200.align", fromlist=["_frames"])._frames(frames)
+    lib, ctx = al._lib, al._ctx
+
+    def step_resident():
+        al.begin(W, H, intr, P)
+        al.set_frames_device(d_frames.data_ptr(), FRAMES, W, W * H)
+        al.preprocess(0, FRAMES)
+        al.align_slots(src_slots, dst_slots, fetch=False)
+        al.copy_results_device(d_poses.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_poses)
+
+    def step_e2e():
+        h_poses[:] = np.eye(4, dtype=np.float32).reshape(16)
+        rc = lib.rst_align_sequence(ctx, fr, FRAMES, C.byref(K), C.byref(P), h_poses.ctypes.data, C.addressof(h_stats))
+        if rc != 0:
+            raise RuntimeError(lib.rst_last_error(ctx).decode())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup):
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                step_fn()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.time()
+            l0 = al.launch_count
+            e0.record(stream)
+            for _ in range(steps):
+                step_fn()
+            e1.record(stream)
+            barrier()
+            t1 = time.time()
+            ms = e0.elapsed_time(e1)
+            launches = al.launch_count - l0
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, t0, t1
+
+    uuid = None
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        pass
+    sampler = ClockSampler(uuid) if rank == 0 else None
+
+    # ---- value: HBM-resident inputs; per-stage events enabled (group boundaries only)
+    al.profile_enable(True)
+    for _ in range(args.warmup):
+        with torch.cuda.stream(stream):
+            step_resident()
+    al.profile_enable(True)   # reset accumulators after warm-up
+    ms_val, launches, t0, t1 = timed(step_resident, args.steps, 0)
+    prof = al.profile_read()
+    al.profile_enable(False)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    total_pairs = world * n_pairs * args.steps
+    value = total_pairs / (ms_val * 1e-3)
+
+    # correctness of what was timed: poses vs ground truth, and (N>1) the gathered block of this rank
+    poses_dev = d_poses.cpu().numpy()
+    from realsensetracker_b200.align import cm_to_pose
+    Tres = cm_to_pose(poses_dev)
+    errs = np.array([synth.pose_error(Tres[i], gt[i]) for i in range(n_pairs)])
+    if world > 1:
+        mine = d_all[rank * n_pairs:(rank + 1) * n_pairs].cpu().numpy()
+        assert np.array_equal(mine, poses_dev), "all_gather block differs from the local result"
+
+    # ---- e2e: pinned host frames in, poses + stats out, every step
+    ms_e2e, launches_e2e, _, _ = timed(step_e2e, args.steps, args.warmup)
+    e2e_value = total_pairs / (ms_e2e * 1e-3)
+    Te2e = cm_to_pose(h_poses)
+    assert np.array_equal(Te2e, Tres), "host-path and device-resident results differ"
+    status_bad = sum(1 for s in h_stats if s.status != 0)
+    mean_count = float(np.mean([s.count for s in h_stats]))
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        npx = W * H
+        n_l0 = prof.launches_icp[0]
+        t_l0 = prof.ms_icp[0] * 1e-3 / max(n_l0, 1)                    # average level-0 launch, seconds
+        bytes_layout = n_pairs * (2.0 * npx + 16.0 * mean_count)       # this layout's compulsory bytes per launch
+        bytes_survey = n_pairs * float(SURVEY_BYTES_PER_PX) * npx      # SURVEY.md §8(d) figure per launch
+        ach = bytes_layout / t_l0 / 1e9
+        ach_s = bytes_survey / t_l0 / 1e9
+        tr = ncu_traffic()
+        icp_ms = sum(prof.ms_icp[l] for l in range(3))
+        pre_ms = sum(prof.ms_preprocess[l] for l in range(3))
+        roofline = {
+            "kernel": "k_icp_iter<level 0> (fused association + point-to-plane J^T J / J^T r + reduction + solve)",
+            "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": (tr or {}).get("dram_bytes_per_launch"),
+            "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": bytes_layout,
+            "bytes_per_px": {"src_depth": 2, "dst_geometry_gather": 16, "associated_px_per_pair": mean_count},
+            "avg_launch_us": t_l0 * 1e6, "launches_timed": n_l0,
+            "survey_equiv": {"bytes_per_px": SURVEY_BYTES_PER_PX, "achieved": ach_s, "frac": ach_s / peak},
+            "stage_share_of_step": {"icp_l0": prof.ms_icp[0] / ms_val, "icp_l1": prof.ms_icp[1] / ms_val,
+                                    "icp_l2": prof.ms_icp[2] / ms_val, "preprocess": pre_ms / ms_val,
+                                    "other": max(0.0, 1.0 - (icp_ms + pre_ms) / ms_val)},
+        }
+        # CPU baseline (bounded sample) — rank 0, N=1 only
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cores = host_cores()
+            n_cpu = max(8, min(cores, n_pairs))
+            rate, dt, Tc, ok = cpu_reference_rate(frames, intr, n_cpu, cores)
+            cerr = np.array([synth.pose_error(Tc[i], gt[i]) for i in range(n_cpu)])
+            from oracle import oracle as O
+            t0n = time.perf_counter()
+            O.align_pair(frames[1], frames[0], intr, O.default_params())
+            dtn = time.perf_counter() - t0n
+            cpu = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
+                   "sample": f"Oracle-R (reference AlignIcp3d path: voxel 0.05, 128 it) on the first {n_cpu} pairs of the "
+                             f"same sequence, one pair per thread, {dt:.1f} s wall",
+                   "pose_err_vs_gt": {"t_m_max": float(cerr[:, 0].max()), "r_rad_max": float(cerr[:, 1].max())},
+                   "same_algorithm_port_1thread_pairs_per_s": 1.0 / dtn}
+        h2d = FRAMES * H * W * 2 + n_pairs * (8 + 64)
+        d2h = n_pairs * (64 + C.sizeof(N.Stats))
+        line = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_val / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "seq640x480_f2f_3level_icp (BASELINE.json configs[1])", "width": W, "height": H,
+                       "frames_per_gpu_per_step": FRAMES, "pairs_per_gpu_per_step": n_pairs, "levels": 3,
+                       "iters_fine_to_coarse": list(ITERS), "accumulation": "fp32 per block (<=2048 px), fp64 across blocks and in the solve",
+                       "l2_policy": f"inputs larger than L2: {FRAMES * npx * (2 + 16) * 1.3125 / 1e6:.0f} MB of depth pyramid + geometry maps streamed per step (L2 = 126 MB)",
+                       "parallelism": f"pairs sharded, {world} rank(s), NCCL all_gather of poses only"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "pose_err_vs_gt": {"t_m_max": float(errs[:, 0].max()), "r_rad_max": float(errs[:, 1].max()),
+                               "pairs_failed": status_bad},
+        }
+        print(json.dumps(line), flush=True)
+    al.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -232,6 +232,25 @@ int32_t rst_evaluate(rst_ctx* ctx, int32_t src_slot, int32_t dst_slot,
 /* Number of kernel launches this context has issued so far (bench evidence). */
 int64_t rst_launch_count(const rst_ctx* ctx);
 
+/* Copies the results of the last rst_align_slots into caller DEVICE buffers
+ * (n_pairs x 16 fp32, n_pairs x rst_stats; either may be NULL), asynchronously on
+ * the context stream — e.g. into the send buffer of an NCCL all-gather. */
+int32_t rst_copy_results_device(rst_ctx* ctx, float* d_poses_out, rst_stats* d_stats_out);
+
+/* Per-stage device timing with CUDA events on the context stream. Events bracket each
+ * GROUP of launches (one pre-processing launch per level; all iterations of one pyramid
+ * level), so enabling it does not perturb the launch sequence. */
+typedef struct rst_profile {
+  float ms_preprocess[RST_MAX_LEVELS];       /* K1+K2+K6, per level, summed since enable */
+  float ms_icp[RST_MAX_LEVELS];              /* K3+K4+K5, per level, summed since enable */
+  int32_t launches_preprocess[RST_MAX_LEVELS];
+  int32_t launches_icp[RST_MAX_LEVELS];
+  int64_t frames_preprocessed[RST_MAX_LEVELS]; /* frames covered by those launches      */
+  int64_t pairs_iterated[RST_MAX_LEVELS];      /* sum over launches of pairs per launch */
+} rst_profile;
+int32_t rst_profile_enable(rst_ctx* ctx, int32_t on); /* also resets the accumulators */
+int32_t rst_profile_read(rst_ctx* ctx, rst_profile* out); /* synchronises the stream  */
+
 #ifdef __cplusplus
 }
 #endif

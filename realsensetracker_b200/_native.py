@@ -48,12 +48,19 @@ class Stats(C.Structure):
                 ("sum_wr2", C.c_double), ("A", C.c_double * 21), ("b", C.c_double * 6)]
 
 
+class Profile(C.Structure):
+    _fields_ = [("ms_preprocess", C.c_float * RST_MAX_LEVELS), ("ms_icp", C.c_float * RST_MAX_LEVELS),
+                ("launches_preprocess", C.c_int32 * RST_MAX_LEVELS), ("launches_icp", C.c_int32 * RST_MAX_LEVELS),
+                ("frames_preprocessed", C.c_int64 * RST_MAX_LEVELS), ("pairs_iterated", C.c_int64 * RST_MAX_LEVELS)]
+
+
 # every symbol include/rst_align.h declares (tests check the library exports all of them)
 ALIGN_SYMBOLS = [
     "rst_ctx_create", "rst_ctx_destroy", "rst_last_error", "rst_last_create_error", "rst_abi_version",
     "rst_params_default", "rst_align_pairs", "rst_align_sequence", "rst_begin", "rst_upload_frames",
     "rst_set_frames_device", "rst_preprocess", "rst_align_slots", "rst_device_results", "rst_sync",
     "rst_level_info", "rst_read_depth", "rst_read_geometry", "rst_evaluate", "rst_launch_count",
+    "rst_copy_results_device", "rst_profile_enable", "rst_profile_read",
 ]
 
 _align = None
@@ -115,6 +122,12 @@ def align_lib() -> C.CDLL:
         lib.rst_evaluate.restype = C.c_int32
         lib.rst_launch_count.argtypes = [C.c_void_p]
         lib.rst_launch_count.restype = C.c_int64
+        lib.rst_copy_results_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.rst_copy_results_device.restype = C.c_int32
+        lib.rst_profile_enable.argtypes = [C.c_void_p, C.c_int32]
+        lib.rst_profile_enable.restype = C.c_int32
+        lib.rst_profile_read.argtypes = [C.c_void_p, P(Profile)]
+        lib.rst_profile_read.restype = C.c_int32
         _align = lib
     return _align
 

@@ -172,6 +172,17 @@ class Aligner:
                                            idx.ctypes.data if want_idx else None, C.byref(st)))
         return idx, st
 
+    def copy_results_device(self, d_poses_ptr: int | None, d_stats_ptr: int | None = None):
+        self._check(self._lib.rst_copy_results_device(self._ctx, d_poses_ptr, d_stats_ptr))
+
+    def profile_enable(self, on: bool = True):
+        self._check(self._lib.rst_profile_enable(self._ctx, 1 if on else 0))
+
+    def profile_read(self) -> "N.Profile":
+        p = N.Profile()
+        self._check(self._lib.rst_profile_read(self._ctx, C.byref(p)))
+        return p
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.rst_launch_count(self._ctx))

@@ -66,7 +66,35 @@ struct rst_ctx {
   int n_pairs_last = 0;
   int64_t launches = 0;
   std::string err;
+
+  // per-stage event timing (rst_profile_*)
+  struct ProfRec { int kind, level, launches; int64_t units; cudaEvent_t e0, e1; };
+  bool profiling = false;
+  std::vector<ProfRec> prof_open;
+  std::vector<cudaEvent_t> ev_pool;
+  rst_profile prof{};
 };
+
+static cudaEvent_t prof_event(rst_ctx* c) {
+  cudaEvent_t e = nullptr;
+  if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+  else cudaEventCreate(&e);
+  return e;
+}
+/* kind 0 = preprocess, 1 = icp */
+static int prof_begin(rst_ctx* c, int kind, int level) {
+  if (!c->profiling) return -1;
+  rst_ctx::ProfRec r{kind, level, 0, 0, prof_event(c), prof_event(c)};
+  cudaEventRecord(r.e0, c->stream);
+  c->prof_open.push_back(r);
+  return (int)c->prof_open.size() - 1;
+}
+static void prof_end(rst_ctx* c, int h, int launches, int64_t units) {
+  if (h < 0) return;
+  c->prof_open[h].launches = launches;
+  c->prof_open[h].units = units;
+  cudaEventRecord(c->prof_open[h].e1, c->stream);
+}
 
 static thread_local std::string g_create_err;
 
@@ -134,6 +162,8 @@ void rst_ctx_destroy(rst_ctx* c) {
   cudaFree(c->d_poses_cm); cudaFree(c->d_stats); cudaFree(c->d_tickets); cudaFree(c->d_partials);
   cudaFree(c->d_idx);
   cudaFreeHost(c->h_pairs); cudaFreeHost(c->h_poses); cudaFreeHost(c->h_stats);
+  for (auto& r : c->prof_open) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -320,7 +350,9 @@ static int32_t preprocess_impl(rst_ctx* c, int first_slot, int n, bool write_geo
     a.first_slot = first_slot;
     a.depth_scale = c->P.depth_scale; a.z_min = c->P.z_min; a.z_max = c->P.z_max;
     a.normal_depth_tol = c->P.normal_depth_tol; a.pyr_tol = c->P.pyr_depth_tol;
+    const int ph = prof_begin(c, 0, l);
     RST_CUDA(c, launch_preprocess(a, n, c->stream));
+    prof_end(c, ph, 1, n);
     c->launches += 1;
   }
   return RST_OK;
@@ -389,14 +421,18 @@ int32_t rst_align_slots(rst_ctx* c, const int32_t* src_slots, const int32_t* dst
   for (int l = c->num_levels - 1; l >= 0; --l) {
     IcpArgs a{};
     fill_icp_args(c, l, &a);
+    const int ph = prof_begin(c, 1, l);
+    int nl = 0;
     for (int it = 0; it < c->P.iters[l]; ++it) {
       for (int off = 0; off < n_pairs; off += 65535) {
         a.pair_offset = off;
         const int cnt = n_pairs - off < 65535 ? n_pairs - off : 65535;
         RST_CUDA(c, launch_icp_iter(a, cnt, c->P.robust_kind, ngate, false, c->stream));
         c->launches += 1;
+        ++nl;
       }
     }
+    prof_end(c, ph, nl, (int64_t)n_pairs * c->P.iters[l]);
   }
   if (poses_inout || stats_out) {
     if (poses_inout)
@@ -414,6 +450,45 @@ int32_t rst_device_results(rst_ctx* c, const float** d_poses, const rst_stats** 
   if (!c) return RST_ERR_INVALID_ARG;
   if (d_poses) *d_poses = c->d_poses_cm;
   if (d_stats) *d_stats = c->d_stats;
+  return RST_OK;
+}
+
+int32_t rst_copy_results_device(rst_ctx* c, float* d_poses_out, rst_stats* d_stats_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  RST_CUDA(c, cudaSetDevice(c->device));
+  const int n = c->n_pairs_last;
+  if (n <= 0) return RST_OK;
+  if (d_poses_out)
+    RST_CUDA(c, cudaMemcpyAsync(d_poses_out, c->d_poses_cm, sizeof(float) * 16 * n, cudaMemcpyDeviceToDevice, c->stream));
+  if (d_stats_out)
+    RST_CUDA(c, cudaMemcpyAsync(d_stats_out, c->d_stats, sizeof(rst_stats) * n, cudaMemcpyDeviceToDevice, c->stream));
+  return RST_OK;
+}
+
+int32_t rst_profile_enable(rst_ctx* c, int32_t on) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  RST_CUDA(c, cudaSetDevice(c->device));
+  RST_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (auto& r : c->prof_open) { c->ev_pool.push_back(r.e0); c->ev_pool.push_back(r.e1); }
+  c->prof_open.clear();
+  std::memset(&c->prof, 0, sizeof(c->prof));
+  c->profiling = on != 0;
+  return RST_OK;
+}
+
+int32_t rst_profile_read(rst_ctx* c, rst_profile* out) {
+  if (!c || !out) return RST_ERR_INVALID_ARG;
+  RST_CUDA(c, cudaSetDevice(c->device));
+  RST_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (auto& r : c->prof_open) {
+    float ms = 0.f;
+    RST_CUDA(c, cudaEventElapsedTime(&ms, r.e0, r.e1));
+    if (r.kind == 0) { c->prof.ms_preprocess[r.level] += ms; c->prof.launches_preprocess[r.level] += r.launches; c->prof.frames_preprocessed[r.level] += r.units; }
+    else { c->prof.ms_icp[r.level] += ms; c->prof.launches_icp[r.level] += r.launches; c->prof.pairs_iterated[r.level] += r.units; }
+    c->ev_pool.push_back(r.e0); c->ev_pool.push_back(r.e1);
+  }
+  c->prof_open.clear();
+  *out = c->prof;
   return RST_OK;
 }
 
