@@ -159,15 +159,15 @@ void on_evaluate(const uint16_t* src_D, const float* src_G, const float* dst_G, 
       const float iz = 1.0f / qz_;
       const float uf = fmaf(L->fx, qx_ * iz, L->cx);
       const float vf = fmaf(L->fy, qy_ * iz, L->cy);
-      if (!(uf > -1.0f && uf < fw && vf > -1.0f && vf < fh)) continue;
+      /* rint() of [-0.5, w-0.5) is always in [0, w-1]: -0.5 rounds to -0, w-0.5 is excluded */
+      if (!(uf >= -0.5f && uf < fw - 0.5f && vf >= -0.5f && vf < fh - 0.5f)) continue;
       const int ui = (int)rintf(uf), vi = (int)rintf(vf);
-      if (ui < 0 || ui >= w || vi < 0 || vi >= h) continue;
       const float* g = dst_G + 4 * ((size_t)vi * w + ui);
       const float gz = g[3];
       if (!(gz > 0.0f)) continue;
       const float nx = g[0], ny = g[1], nz = g[2];
       const float kxq = ((float)ui - L->cx) * L->ifx, kyq = ((float)vi - L->cy) * L->ify;
-      const float dx = qx_ - kxq * gz, dy = qy_ - kyq * gz, dz = qz_ - gz;
+      const float dx = fmaf(-kxq, gz, qx_), dy = fmaf(-kyq, gz, qy_), dz = qz_ - gz;
       const float dist2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
       if (!(dist2 <= dmax2)) continue;
       if (use_ngate) {

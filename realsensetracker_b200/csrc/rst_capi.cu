@@ -34,6 +34,8 @@ struct rst_ctx {
   int64_t dframe[RST_MAX_LEVELS]{};
   int64_t gframe[RST_MAX_LEVELS]{};
   int blocks_per_pair[RST_MAX_LEVELS]{}, chunks_per_row[RST_MAX_LEVELS]{}, n_chunks[RST_MAX_LEVELS]{};
+  int groups[RST_MAX_LEVELS]{};
+  uint32_t d_lo = 1, d_span = 0;
 
   // HBM frame store (allocated once for max_w x max_h x max_frames)
   uint16_t* d_depth[RST_MAX_LEVELS]{};
@@ -265,7 +267,20 @@ int32_t rst_begin(rst_ctx* c, int32_t width, int32_t height, const rst_intrinsic
     c->gframe[l] = (int64_t)c->geom[l].w * c->geom[l].h;
     c->chunks_per_row[l] = (c->geom[l].w + kChunkPx - 1) / kChunkPx;
     c->n_chunks[l] = c->chunks_per_row[l] * c->geom[l].h;
-    c->blocks_per_pair[l] = (c->n_chunks[l] + kChunksPerBlock - 1) / kChunksPerBlock;
+    // block extent depends on the image size only, so results never depend on the batch size
+    c->groups[l] = c->n_chunks[l] >= 64 * kChunksPerBlock ? 4 : 1;
+    const int cpb = kChunksPerBlock * c->groups[l];
+    c->blocks_per_pair[l] = (c->n_chunks[l] + cpb - 1) / cpb;
+  }
+  {
+    // integer form of the depth validity test: d != 0 && z_min <= float(d)*scale <= z_max (monotone in d)
+    uint32_t lo = 65536u, hi = 0u;
+    for (uint32_t d = 1; d <= 65535u; ++d) {
+      const float z = (float)d * P.depth_scale;
+      if (z >= P.z_min && z <= P.z_max) { if (d < lo) lo = d; hi = d; }
+    }
+    if (hi < lo) return fail(c, RST_ERR_INVALID_ARG, "no uint16 depth value falls inside [z_min, z_max]");
+    c->d_lo = lo; c->d_span = hi - lo;
   }
   if (!same || c->store_dirty) {
     // row padding (columns >= w) must read as invalid depth
@@ -378,7 +393,11 @@ static void fill_icp_args(const rst_ctx* c, int l, IcpArgs* a) {
   a->blocks_per_pair = c->blocks_per_pair[l];
   a->chunks_per_row = c->chunks_per_row[l];
   a->n_chunks = c->n_chunks[l];
-  a->depth_scale = c->P.depth_scale; a->z_min = c->P.z_min; a->z_max = c->P.z_max;
+  a->groups = c->groups[l];
+  a->cpr_magic = (uint32_t)(((1ull << 32) + (uint64_t)c->chunks_per_row[l] - 1) / (uint64_t)c->chunks_per_row[l]);
+  a->d_lo = c->d_lo; a->d_span = c->d_span;
+  a->umax = (float)c->geom[l].w - 0.5f; a->vmax = (float)c->geom[l].h - 0.5f;
+  a->depth_scale = c->P.depth_scale;
   a->dmax2 = c->P.dist_max * c->P.dist_max;
   a->ncos_min = c->P.normal_cos_min;
   a->robust_scale = c->P.robust_scale;

@@ -68,7 +68,11 @@ struct IcpArgs {
   uint32_t* tickets;          // [pair]
   int32_t max_blocks;
   int32_t blocks_per_pair, chunks_per_row, n_chunks;
-  float depth_scale, z_min, z_max, dmax2, ncos_min, robust_scale;
+  int32_t groups;             // groups of kChunksPerBlock chunks per block
+  uint32_t cpr_magic;         // ceil(2^32 / chunks_per_row): c / chunks_per_row == umulhi(c, magic)
+  uint32_t d_lo, d_span;      // valid raw depth: (d - d_lo) <= d_span  <=>  d != 0 && z_min <= d*scale <= z_max
+  float umax, vmax;           // w - 0.5, h - 0.5
+  float depth_scale, dmax2, ncos_min, robust_scale;
   /* finalize */
   double* pose_master;        // 12 per pair
   float* pose_f32_out;        // == pose_f32 (written by the last block)
