@@ -155,7 +155,7 @@ void on_evaluate(const uint16_t* src_D, const float* src_G, const float* dst_G, 
       const float qx_ = fmaf(R00, px, fmaf(R01, py, fmaf(R02, pz, tx)));
       const float qy_ = fmaf(R10, px, fmaf(R11, py, fmaf(R12, pz, ty)));
       const float qz_ = fmaf(R20, px, fmaf(R21, py, fmaf(R22, pz, tz)));
-      if (!(qz_ > 0.0f)) continue;
+      if (!(qz_ >= 1e-6f)) continue; /* also keeps 1/qz in the normal range */
       const float iz = 1.0f / qz_;
       const float uf = fmaf(L->fx, qx_ * iz, L->cx);
       const float vf = fmaf(L->fy, qy_ * iz, L->cy);

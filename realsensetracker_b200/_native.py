@@ -68,7 +68,10 @@ _synth = None
 
 
 def _load(name: str) -> C.CDLL:
+    import os
     path = LIBDIR / name
+    if name == "librst_align.so" and os.environ.get("RST_ALIGN_LIB"):  # kernel-variant experiments
+        path = Path(os.environ["RST_ALIGN_LIB"])
     if not path.exists():
         raise ImportError(
             f"{path} is missing — build it with `python -m realsensetracker_b200.build` "

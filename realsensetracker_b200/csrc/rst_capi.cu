@@ -268,7 +268,7 @@ int32_t rst_begin(rst_ctx* c, int32_t width, int32_t height, const rst_intrinsic
     c->chunks_per_row[l] = (c->geom[l].w + kChunkPx - 1) / kChunkPx;
     c->n_chunks[l] = c->chunks_per_row[l] * c->geom[l].h;
     // block extent depends on the image size only, so results never depend on the batch size
-    c->groups[l] = c->n_chunks[l] >= 64 * kChunksPerBlock ? 4 : 1;
+    c->groups[l] = c->n_chunks[l] * kChunkPx >= 8 * RST_ICP_GROUP_PX ? RST_ICP_GROUP_PX / (kChunksPerBlock * kChunkPx) : 1;
     const int cpb = kChunksPerBlock * c->groups[l];
     c->blocks_per_pair[l] = (c->n_chunks[l] + cpb - 1) / cpb;
   }

@@ -26,9 +26,22 @@ namespace rst {
 
 constexpr int kAcc = 29;          // 21 (A upper) + 6 (b) + sum w r^2 + count
 constexpr int kAccPad = 32;       // partial row stride (floats)
-constexpr int kIcpThreads = 256;
+#ifndef RST_ICP_THREADS
+#define RST_ICP_THREADS 128
+#endif
+#ifndef RST_ICP_CPW
+#define RST_ICP_CPW 4
+#endif
+#ifndef RST_ICP_MINB
+#define RST_ICP_MINB 4
+#endif
+#ifndef RST_ICP_GROUP_PX
+#define RST_ICP_GROUP_PX 8192     // pixels per block on large levels (groups = this / block pixels per group)
+#endif
+constexpr int kIcpThreads = RST_ICP_THREADS;
 constexpr int kChunkPx = 64;      // pixels one warp covers per step (2 per lane)
-constexpr int kChunksPerWarp = 4; // steps per warp -> 8 pixels per thread
+constexpr int kChunksPerWarp = RST_ICP_CPW; // chunks per warp per group -> 2*CPW pixels in flight per thread
+constexpr float kMinProjZ = 1e-6f; // transformed points closer than this to the camera plane are rejected
 constexpr int kChunksPerBlock = (kIcpThreads / 32) * kChunksPerWarp;  // 32 -> 2048 px
 constexpr int kTileW = 64, kTileH = 32;  // preprocess tile
 
