@@ -201,6 +201,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
 
     stream = torch.cuda.Stream(device=dev)
     al = Aligner(W, H, FRAMES, n_pairs, device=local_rank, stream=stream.cuda_stream)
+    if args.chunk is not None:
+        al.set_pipeline_chunk(args.chunk)
     src_slots = np.arange(1, FRAMES, dtype=np.int32)
     dst_slots = np.arange(0, FRAMES - 1, dtype=np.int32)
     d_poses = torch.empty((n_pairs, 16), dtype=torch.float32, device=dev)
@@ -365,6 +367,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--chunk", type=int, default=None, help="frames per upload/compute chunk of the e2e path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

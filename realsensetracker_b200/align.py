@@ -172,6 +172,9 @@ class Aligner:
                                            idx.ctypes.data if want_idx else None, C.byref(st)))
         return idx, st
 
+    def set_pipeline_chunk(self, frames_per_chunk: int):
+        self._check(self._lib.rst_set_pipeline_chunk(self._ctx, frames_per_chunk))
+
     def copy_results_device(self, d_poses_ptr: int | None, d_stats_ptr: int | None = None):
         self._check(self._lib.rst_copy_results_device(self._ctx, d_poses_ptr, d_stats_ptr))
 

@@ -65,6 +65,8 @@ struct rst_ctx {
   float* h_poses = nullptr;
   rst_stats* h_stats = nullptr;
 
+  cudaStream_t copy_stream = nullptr;   // H2D of the next chunk overlaps compute of the current one
+  int pipeline_chunk = 32;              // frames (pairs) per upload/compute chunk of the host entry points
   int n_pairs_last = 0;
   int64_t launches = 0;
   std::string err;
@@ -166,6 +168,7 @@ void rst_ctx_destroy(rst_ctx* c) {
   cudaFreeHost(c->h_pairs); cudaFreeHost(c->h_poses); cudaFreeHost(c->h_stats);
   for (auto& r : c->prof_open) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -211,6 +214,7 @@ int32_t rst_ctx_create(int32_t device, int32_t max_w, int32_t max_h, int32_t max
   CREATE_TRY(cudaSetDevice(device));
   if (stream) { c->stream = (cudaStream_t)stream; }
   else { CREATE_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  CREATE_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   int w = max_w, h = max_h;
   for (int l = 0; l < RST_MAX_LEVELS; ++l) {
     const size_t px = (size_t)round_up(w, 8) * h;
@@ -411,22 +415,16 @@ static void fill_icp_args(const rst_ctx* c, int l, IcpArgs* a) {
   a->idx_out = nullptr;
 }
 
-int32_t rst_align_slots(rst_ctx* c, const int32_t* src_slots, const int32_t* dst_slots, int32_t n_pairs,
-                        float* poses_inout, rst_stats* stats_out) {
-  if (!c) return RST_ERR_INVALID_ARG;
-  if (!c->begun) return fail(c, RST_ERR_INVALID_ARG, "rst_begin has not been called");
-  if (!src_slots || !dst_slots || n_pairs < 0) return fail(c, RST_ERR_INVALID_ARG, "bad slot arrays / n_pairs");
-  if (n_pairs > c->max_pairs) return fail(c, RST_ERR_CAPACITY, "more pairs than the context holds");
-  c->n_pairs_last = n_pairs;
-  if (n_pairs == 0) return RST_OK;
-  RST_CUDA(c, cudaSetDevice(c->device));
+/* stage 1 of an alignment: pair table + initial poses -> device, state reset */
+static int32_t pairs_begin(rst_ctx* c, const int32_t* src_slots, const int32_t* dst_slots, int32_t n_pairs,
+                           const float* poses_in) {
   for (int i = 0; i < n_pairs; ++i) {
     if (src_slots[i] < 0 || src_slots[i] >= c->max_frames || dst_slots[i] < 0 || dst_slots[i] >= c->max_frames)
       return fail(c, RST_ERR_INVALID_ARG, "slot index out of range");
     c->h_pairs[i] = make_int2(src_slots[i], dst_slots[i]);
   }
-  if (poses_inout) {
-    std::memcpy(c->h_poses, poses_inout, sizeof(float) * 16 * n_pairs);
+  if (poses_in) {
+    std::memcpy(c->h_poses, poses_in, sizeof(float) * 16 * n_pairs);
   } else {
     for (int i = 0; i < n_pairs; ++i)
       for (int k = 0; k < 16; ++k) c->h_poses[16 * i + k] = (k % 5 == 0) ? 1.f : 0.f;
@@ -436,6 +434,13 @@ int32_t rst_align_slots(rst_ctx* c, const int32_t* src_slots, const int32_t* dst
   InitArgs ia{c->d_poses_in, c->d_master, c->d_pose_f32, c->d_poses_cm, c->d_stats, c->d_tickets, n_pairs};
   RST_CUDA(c, launch_init_pairs(ia, c->stream));
   c->launches += 1;
+  c->n_pairs_last = n_pairs;
+  return RST_OK;
+}
+
+/* stage 2: the whole coarse-to-fine schedule for pairs [first, first + n) */
+static int32_t pairs_iterate(rst_ctx* c, int first, int n) {
+  if (n <= 0) return RST_OK;
   const bool ngate = c->P.normal_cos_min > -1.0f;
   for (int l = c->num_levels - 1; l >= 0; --l) {
     IcpArgs a{};
@@ -443,25 +448,50 @@ int32_t rst_align_slots(rst_ctx* c, const int32_t* src_slots, const int32_t* dst
     const int ph = prof_begin(c, 1, l);
     int nl = 0;
     for (int it = 0; it < c->P.iters[l]; ++it) {
-      for (int off = 0; off < n_pairs; off += 65535) {
-        a.pair_offset = off;
-        const int cnt = n_pairs - off < 65535 ? n_pairs - off : 65535;
+      for (int off = 0; off < n; off += 65535) {
+        a.pair_offset = first + off;
+        const int cnt = n - off < 65535 ? n - off : 65535;
         RST_CUDA(c, launch_icp_iter(a, cnt, c->P.robust_kind, ngate, false, c->stream));
         c->launches += 1;
         ++nl;
       }
     }
-    prof_end(c, ph, nl, (int64_t)n_pairs * c->P.iters[l]);
+    prof_end(c, ph, nl, (int64_t)n * c->P.iters[l]);
   }
-  if (poses_inout || stats_out) {
-    if (poses_inout)
-      RST_CUDA(c, cudaMemcpyAsync(c->h_poses, c->d_poses_cm, sizeof(float) * 16 * n_pairs, cudaMemcpyDeviceToHost, c->stream));
-    if (stats_out)
-      RST_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(rst_stats) * n_pairs, cudaMemcpyDeviceToHost, c->stream));
-    RST_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (poses_inout) std::memcpy(poses_inout, c->h_poses, sizeof(float) * 16 * n_pairs);
-    if (stats_out) std::memcpy(stats_out, c->h_stats, sizeof(rst_stats) * n_pairs);
-  }
+  return RST_OK;
+}
+
+/* stage 3: results -> host (blocks until the stream has drained) */
+static int32_t pairs_fetch(rst_ctx* c, int32_t n_pairs, float* poses_out, rst_stats* stats_out) {
+  if (!poses_out && !stats_out) return RST_OK;
+  if (poses_out)
+    RST_CUDA(c, cudaMemcpyAsync(c->h_poses, c->d_poses_cm, sizeof(float) * 16 * n_pairs, cudaMemcpyDeviceToHost, c->stream));
+  if (stats_out)
+    RST_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(rst_stats) * n_pairs, cudaMemcpyDeviceToHost, c->stream));
+  RST_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (poses_out) std::memcpy(poses_out, c->h_poses, sizeof(float) * 16 * n_pairs);
+  if (stats_out) std::memcpy(stats_out, c->h_stats, sizeof(rst_stats) * n_pairs);
+  return RST_OK;
+}
+
+int32_t rst_align_slots(rst_ctx* c, const int32_t* src_slots, const int32_t* dst_slots, int32_t n_pairs,
+                        float* poses_inout, rst_stats* stats_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  if (!c->begun) return fail(c, RST_ERR_INVALID_ARG, "rst_begin has not been called");
+  if (!src_slots || !dst_slots || n_pairs < 0) return fail(c, RST_ERR_INVALID_ARG, "bad slot arrays / n_pairs");
+  if (n_pairs > c->max_pairs) return fail(c, RST_ERR_CAPACITY, "more pairs than the context holds");
+  c->n_pairs_last = n_pairs;
+  if (n_pairs == 0) return RST_OK;
+  RST_CUDA(c, cudaSetDevice(c->device));
+  int32_t rc;
+  if ((rc = pairs_begin(c, src_slots, dst_slots, n_pairs, poses_inout)) != RST_OK) return rc;
+  if ((rc = pairs_iterate(c, 0, n_pairs)) != RST_OK) return rc;
+  return pairs_fetch(c, n_pairs, poses_inout, stats_out);
+}
+
+int32_t rst_set_pipeline_chunk(rst_ctx* c, int32_t frames_per_chunk) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  c->pipeline_chunk = frames_per_chunk > 0 ? frames_per_chunk : 0;
   return RST_OK;
 }
 
@@ -524,6 +554,29 @@ static int32_t check_frames(rst_ctx* c, const rst_frame* f, int n) {
   return RST_OK;
 }
 
+/* Uploads frames [f0, f1) on the copy stream and makes the compute stream wait for them. */
+static int32_t upload_chunk(rst_ctx* c, const rst_frame* frames, int n, int first_slot) {
+  cudaStream_t compute = c->stream;
+  c->stream = c->copy_stream;                       // rst_upload_frames copies on c->stream
+  const int32_t rc = rst_upload_frames(c, frames, n, first_slot);
+  c->stream = compute;
+  if (rc != RST_OK) return rc;
+  cudaEvent_t e = prof_event(c);
+  RST_CUDA(c, cudaEventRecord(e, c->copy_stream));
+  RST_CUDA(c, cudaStreamWaitEvent(c->stream, e, 0));
+  c->ev_pool.push_back(e);                          // safe to recycle: the wait is already enqueued
+  return RST_OK;
+}
+
+/* the copy stream must not overwrite frame slots that earlier compute work still reads */
+static int32_t copy_after_compute(rst_ctx* c) {
+  cudaEvent_t e = prof_event(c);
+  RST_CUDA(c, cudaEventRecord(e, c->stream));
+  RST_CUDA(c, cudaStreamWaitEvent(c->copy_stream, e, 0));
+  c->ev_pool.push_back(e);
+  return RST_OK;
+}
+
 int32_t rst_align_pairs(rst_ctx* c, const rst_frame* src, const rst_frame* dst, int32_t n_pairs,
                         const rst_intrinsics* intr, const rst_params* params, float* poses_inout,
                         rst_stats* stats_out) {
@@ -535,14 +588,22 @@ int32_t rst_align_pairs(rst_ctx* c, const rst_frame* src, const rst_frame* dst, 
   if ((rc = check_frames(c, src, n_pairs)) != RST_OK) return rc;
   if ((rc = rst_begin(c, src[0].width, src[0].height, intr, params)) != RST_OK) return rc;
   // dst frames in slots [0, n), src frames in [n, 2n)
-  if ((rc = rst_upload_frames(c, dst, n_pairs, 0)) != RST_OK) return rc;
-  if ((rc = rst_upload_frames(c, src, n_pairs, n_pairs)) != RST_OK) return rc;
-  if ((rc = preprocess_impl(c, 0, n_pairs, true)) != RST_OK) return rc;
-  const bool ngate = c->P.normal_cos_min > -1.0f;
-  if ((rc = preprocess_impl(c, n_pairs, n_pairs, ngate)) != RST_OK) return rc;
   std::vector<int32_t> s(n_pairs), d(n_pairs);
   for (int i = 0; i < n_pairs; ++i) { d[i] = i; s[i] = n_pairs + i; }
-  return rst_align_slots(c, s.data(), d.data(), n_pairs, poses_inout, stats_out);
+  if ((rc = pairs_begin(c, s.data(), d.data(), n_pairs, poses_inout)) != RST_OK) return rc;
+  if ((rc = copy_after_compute(c)) != RST_OK) return rc;
+  const bool ngate = c->P.normal_cos_min > -1.0f;
+  // chunked so that the H2D copy of chunk k+1 overlaps pre-processing + ICP of chunk k
+  const int chunk = c->pipeline_chunk > 0 ? c->pipeline_chunk : n_pairs;
+  for (int p0 = 0; p0 < n_pairs; p0 += chunk) {
+    const int n = n_pairs - p0 < chunk ? n_pairs - p0 : chunk;
+    if ((rc = upload_chunk(c, dst + p0, n, p0)) != RST_OK) return rc;
+    if ((rc = upload_chunk(c, src + p0, n, n_pairs + p0)) != RST_OK) return rc;
+    if ((rc = preprocess_impl(c, p0, n, true)) != RST_OK) return rc;
+    if ((rc = preprocess_impl(c, n_pairs + p0, n, ngate)) != RST_OK) return rc;
+    if ((rc = pairs_iterate(c, p0, n)) != RST_OK) return rc;
+  }
+  return pairs_fetch(c, n_pairs, poses_inout, stats_out);
 }
 
 int32_t rst_align_sequence(rst_ctx* c, const rst_frame* frames, int32_t n_frames, const rst_intrinsics* intr,
@@ -554,11 +615,21 @@ int32_t rst_align_sequence(rst_ctx* c, const rst_frame* frames, int32_t n_frames
   int32_t rc;
   if ((rc = check_frames(c, frames, n_frames)) != RST_OK) return rc;
   if ((rc = rst_begin(c, frames[0].width, frames[0].height, intr, params)) != RST_OK) return rc;
-  if ((rc = rst_upload_frames(c, frames, n_frames, 0)) != RST_OK) return rc;
-  if ((rc = preprocess_impl(c, 0, n_frames, true)) != RST_OK) return rc;
-  std::vector<int32_t> s(n_frames - 1), d(n_frames - 1);
-  for (int i = 0; i + 1 < n_frames; ++i) { s[i] = i + 1; d[i] = i; }  // AlignIcp3d(curr, prev): rs_replay_app.cpp:251
-  return rst_align_slots(c, s.data(), d.data(), n_frames - 1, poses_inout, stats_out);
+  const int n_pairs = n_frames - 1;
+  std::vector<int32_t> s(n_pairs), d(n_pairs);
+  for (int i = 0; i < n_pairs; ++i) { s[i] = i + 1; d[i] = i; }  // AlignIcp3d(curr, prev): rs_replay_app.cpp:251
+  if ((rc = pairs_begin(c, s.data(), d.data(), n_pairs, poses_inout)) != RST_OK) return rc;
+  if ((rc = copy_after_compute(c)) != RST_OK) return rc;
+  const int chunk = c->pipeline_chunk > 0 ? c->pipeline_chunk : n_frames;
+  for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+    const int n = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+    if ((rc = upload_chunk(c, frames + f0, n, f0)) != RST_OK) return rc;
+    if ((rc = preprocess_impl(c, f0, n, true)) != RST_OK) return rc;
+    // pairs whose two frames are now resident: pair i uses frames i and i+1
+    const int p0 = f0 > 0 ? f0 - 1 : 0, p1 = f0 + n - 1;
+    if ((rc = pairs_iterate(c, p0, p1 - p0)) != RST_OK) return rc;
+  }
+  return pairs_fetch(c, n_pairs, poses_inout, stats_out);
 }
 
 int32_t rst_level_info(const rst_ctx* c, int32_t level, int32_t* width, int32_t* height, int32_t* pitch_px,
