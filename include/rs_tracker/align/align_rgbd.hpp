@@ -1,0 +1,165 @@
+// align_rgbd.hpp — C++ host API of the B200 alignment engine, in the reference's idiom.
+//
+// Frame-based sibling of the reference's
+//   bool AlignIcp3d(const Cloud3f& src, const Cloud3f& dst, const int max_iter,
+//                   Eigen::Isometry3f* const transform);
+//   (rs_tracker/align/include/rs_tracker/align/align_icp.hpp:22-24)
+// Same conventions: free functions in namespace rs_tracker, inputs by const reference, outputs
+// last as `T* const`, `bool` = success, and `transform` is READ as the initial guess and
+// OVERWRITTEN with the result (align_icp.cpp:82,156); it maps src -> dst (align_icp.cpp:107).
+// Frame-level inputs are what the driver delivers (rs_driver.hpp:17-22): CV_16UC1 depth,
+// CV_8UC3 colour, and the 3x3 K of rs_driver.cpp:264-280.
+//
+// Header-only over the C ABI (include/rst_align.h); link with librst_align.so. No Eigen/OpenCV
+// dependency: Pose is 16 floats, column-major, bit-compatible with Eigen::Isometry3f::matrix();
+// when <Eigen/Geometry> is available an Isometry3f overload is provided.
+#pragma once
+
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "rst_align.h"
+
+#if defined(__has_include)
+#if __has_include(<Eigen/Geometry>)
+#include <Eigen/Geometry>
+#define RS_TRACKER_HAVE_EIGEN 1
+#endif
+#endif
+
+namespace rs_tracker {
+
+/// One RGB-D frame as the driver hands it out (rs_driver.hpp:17-19): depth CV_16UC1, colour CV_8UC3.
+struct DepthFrame {
+  const std::uint16_t* depth{nullptr};
+  const std::uint8_t* rgb{nullptr};
+  int width{0}, height{0};
+  int depth_stride_bytes{0};  ///< 0 = tightly packed
+  int rgb_stride_bytes{0};
+  rst_frame c() const {
+    return rst_frame{depth, rgb, width, height, depth_stride_bytes ? depth_stride_bytes : width * 2,
+                     rgb_stride_bytes ? rgb_stride_bytes : width * 3};
+  }
+};
+
+/// Pin-hole intrinsics; FromMatrix takes the column-major 3x3 of RsDriver::GetIntrinsicMatrix()
+/// (rs_driver.cpp:264-280): K = [[fx,0,ppx],[0,fy,ppy],[0,0,1]].
+struct Intrinsics {
+  float fx{0}, fy{0}, cx{0}, cy{0};
+  static Intrinsics FromMatrix(const float* K_colmajor3x3) {
+    return Intrinsics{K_colmajor3x3[0], K_colmajor3x3[4], K_colmajor3x3[6], K_colmajor3x3[7]};
+  }
+  rst_intrinsics c() const { return rst_intrinsics{fx, fy, cx, cy}; }
+};
+
+/// 4x4 rigid transform, column-major fp32 — the memory layout of Eigen::Isometry3f::matrix().
+struct Pose {
+  std::array<float, 16> m{{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}};
+  static Pose Identity() { return Pose{}; }
+  float& operator()(int r, int c) { return m[r + 4 * c]; }
+  float operator()(int r, int c) const { return m[r + 4 * c]; }
+  /// this * other (the replay loop chains total_xfm = total_xfm * xfm, rs_replay_app.cpp:267)
+  Pose operator*(const Pose& o) const {
+    Pose r;
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        float s = 0.f;
+        for (int k = 0; k < 4; ++k) s += (*this)(i, k) * o(k, j);
+        r(i, j) = s;
+      }
+    return r;
+  }
+};
+
+/// Algorithm constants (the reference hard-codes its own, align_icp.cpp:91,96-98,165).
+struct AlignParams : rst_params {
+  AlignParams() { rst_params_default(this); }
+};
+
+using AlignStats = rst_stats;
+
+/// One alignment context per GPU (rst_ctx). Not thread-safe; contexts are independent.
+class AlignContext {
+ public:
+  AlignContext(int device, int max_width, int max_height, int max_frames, int max_pairs, void* stream = nullptr) {
+    const int rc = rst_ctx_create(device, max_width, max_height, max_frames, max_pairs, stream, &ctx_);
+    if (rc != RST_OK) throw std::runtime_error(std::string("rst_ctx_create: ") + rst_last_create_error());
+  }
+  ~AlignContext() { rst_ctx_destroy(ctx_); }
+  AlignContext(const AlignContext&) = delete;
+  AlignContext& operator=(const AlignContext&) = delete;
+  rst_ctx* get() const { return ctx_; }
+  const char* LastError() const { return rst_last_error(ctx_); }
+
+ private:
+  rst_ctx* ctx_{nullptr};
+};
+
+/// Aligns `src` onto `dst`: p_dst ~ transform * p_src. Returns false when the call fails or the
+/// pair's status word is not RST_STATUS_OK (too few associations / degenerate / non-finite —
+/// the reference's `false` for < 3 points, align_icp.cpp:77-79).
+inline bool AlignRgbd(AlignContext& ctx, const DepthFrame& src, const DepthFrame& dst, const Intrinsics& K,
+                      const AlignParams& params, Pose* const transform, AlignStats* const stats = nullptr) {
+  const rst_frame s = src.c(), d = dst.c();
+  const rst_intrinsics k = K.c();
+  AlignStats st{};
+  const int rc = rst_align_pairs(ctx.get(), &s, &d, 1, &k, &params, transform->m.data(), &st);
+  if (stats) *stats = st;
+  return rc == RST_OK && st.status == RST_STATUS_OK;
+}
+
+/// Batched overload: pair i aligns src[i] onto dst[i]; transforms in/out, stats optional.
+/// Returns true when the call ran and every pair succeeded; per-pair status is in `stats`.
+inline bool AlignRgbd(AlignContext& ctx, const std::vector<DepthFrame>& src, const std::vector<DepthFrame>& dst,
+                      const Intrinsics& K, const AlignParams& params, std::vector<Pose>* const transforms,
+                      std::vector<AlignStats>* const stats = nullptr) {
+  const int n = static_cast<int>(src.size());
+  if (dst.size() != src.size() || static_cast<int>(transforms->size()) != n) return false;
+  std::vector<rst_frame> s(n), d(n);
+  for (int i = 0; i < n; ++i) { s[i] = src[i].c(); d[i] = dst[i].c(); }
+  std::vector<AlignStats> st(n);
+  const rst_intrinsics k = K.c();
+  static_assert(sizeof(Pose) == 16 * sizeof(float), "Pose must be 16 packed floats");
+  const int rc = rst_align_pairs(ctx.get(), s.data(), d.data(), n, &k, &params,
+                                 n ? (*transforms)[0].m.data() : nullptr, st.data());
+  bool ok = rc == RST_OK;
+  for (const auto& x : st) ok = ok && x.status == RST_STATUS_OK;
+  if (stats) *stats = std::move(st);
+  return ok;
+}
+
+/// Frame-to-frame odometry over a sequence — the loop body of rs_replay_app.cpp:246-251 for all
+/// consecutive frames at once: (*transforms)[i] = T_{i <- i+1} (AlignIcp3d(curr, prev)).
+inline bool AlignSequence(AlignContext& ctx, const std::vector<DepthFrame>& frames, const Intrinsics& K,
+                          const AlignParams& params, std::vector<Pose>* const transforms,
+                          std::vector<AlignStats>* const stats = nullptr) {
+  const int n = static_cast<int>(frames.size());
+  if (n < 2 || static_cast<int>(transforms->size()) != n - 1) return false;
+  std::vector<rst_frame> f(n);
+  for (int i = 0; i < n; ++i) f[i] = frames[i].c();
+  std::vector<AlignStats> st(n - 1);
+  const rst_intrinsics k = K.c();
+  const int rc = rst_align_sequence(ctx.get(), f.data(), n, &k, &params, (*transforms)[0].m.data(), st.data());
+  bool ok = rc == RST_OK;
+  for (const auto& x : st) ok = ok && x.status == RST_STATUS_OK;
+  if (stats) *stats = std::move(st);
+  return ok;
+}
+
+#ifdef RS_TRACKER_HAVE_EIGEN
+/// Drop-in signature for the reference's call sites (rs_replay_app.cpp:251, rs_align_app.cpp:303).
+inline bool AlignRgbd(AlignContext& ctx, const DepthFrame& src, const DepthFrame& dst, const Eigen::Matrix3f& K,
+                      const AlignParams& params, Eigen::Isometry3f* const transform, AlignStats* const stats = nullptr) {
+  Pose p;
+  std::memcpy(p.m.data(), transform->matrix().data(), sizeof(float) * 16);
+  const bool ok = AlignRgbd(ctx, src, dst, Intrinsics::FromMatrix(K.data()), params, &p, stats);
+  std::memcpy(transform->matrix().data(), p.m.data(), sizeof(float) * 16);
+  return ok;
+}
+#endif
+
+}  // namespace rs_tracker

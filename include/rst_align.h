@@ -165,7 +165,7 @@ int32_t rst_align_sequence(rst_ctx* ctx, const rst_frame* frames, int32_t n_fram
 
 /* The two host-frame calls above upload and process their frames in chunks so that the
  * H2D copy of chunk k+1 (on an internal copy stream) overlaps the kernels of chunk k.
- * `frames_per_chunk` <= 0 disables the chunking (one upload, then one pass). Default 32.
+ * `frames_per_chunk` <= 0 disables the chunking (one upload, then one pass; the default).
  * The chunk size never changes results: every pair is reduced in image-size-determined blocks. */
 int32_t rst_set_pipeline_chunk(rst_ctx* ctx, int32_t frames_per_chunk);
 

@@ -66,7 +66,7 @@ struct rst_ctx {
   rst_stats* h_stats = nullptr;
 
   cudaStream_t copy_stream = nullptr;   // H2D of the next chunk overlaps compute of the current one
-  int pipeline_chunk = 32;              // frames (pairs) per upload/compute chunk of the host entry points
+  int pipeline_chunk = 0;               // frames (pairs) per upload/compute chunk of the host entry points
   int n_pairs_last = 0;
   int64_t launches = 0;
   std::string err;

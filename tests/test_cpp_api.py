@@ -1,0 +1,30 @@
+"""The C++ host API (include/rs_tracker/align/align_rgbd.hpp) over the C ABI: compiles with g++
+(CPU check) and, on the GPU box, the rs_replay_app-style odometry loop runs through it."""
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+EXE = ROOT / "examples" / "replay_synth"
+
+
+def build_example():
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-I", str(ROOT / "include"), "-I", str(ROOT / "realsensetracker_b200" / "csrc"),
+           str(ROOT / "examples" / "replay_synth.cpp"), "-L", str(ROOT / "realsensetracker_b200" / "_lib"),
+           "-lrst_align", "-lrst_synth", "-Wl,-rpath," + str(ROOT / "realsensetracker_b200" / "_lib"), "-o", str(EXE)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return EXE
+
+
+def test_cpp_header_compiles_and_links():
+    build_example()
+
+
+@pytest.mark.gpu
+def test_replay_loop_through_the_cpp_api():
+    exe = build_example()
+    res = subprocess.run([str(exe), "12"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "failures 0" in res.stdout
