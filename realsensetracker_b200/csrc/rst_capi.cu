@@ -41,6 +41,7 @@ struct rst_ctx {
   uint16_t* d_depth[RST_MAX_LEVELS]{};
   size_t depth_bytes[RST_MAX_LEVELS]{};
   float4* d_geom[RST_MAX_LEVELS]{};
+  size_t geom_bytes[RST_MAX_LEVELS]{};
   bool ext0 = false;  // level 0 read in place from caller memory
   const uint16_t* ext_depth0 = nullptr;
   int ext_pitch0 = 0;
@@ -117,6 +118,7 @@ static int fail(rst_ctx* c, int code, const char* msg) {
 }
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+constexpr int kGeomGuard = 8;  // all-zero float4 texels in front of every geometry frame (index -1 = rejected pixel)
 
 /* pyramid level geometry — identical expressions to the CPU specification */
 static void level_geom(const rst_intrinsics& K, int w, int h, int level, LevelGeom* g) {
@@ -220,7 +222,8 @@ int32_t rst_ctx_create(int32_t device, int32_t max_w, int32_t max_h, int32_t max
     const size_t px = (size_t)round_up(w, 8) * h;
     c->depth_bytes[l] = px * sizeof(uint16_t) * max_frames;
     CREATE_TRY(cudaMalloc(&c->d_depth[l], c->depth_bytes[l]));
-    CREATE_TRY(cudaMalloc(&c->d_geom[l], (size_t)w * h * sizeof(float4) * max_frames));
+    c->geom_bytes[l] = ((size_t)w * h + kGeomGuard) * sizeof(float4) * max_frames + kGeomGuard * sizeof(float4);
+    CREATE_TRY(cudaMalloc(&c->d_geom[l], c->geom_bytes[l]));
     w /= 2; h /= 2;
     if (w < 1) w = 1;
     if (h < 1) h = 1;
@@ -268,7 +271,7 @@ int32_t rst_begin(rst_ctx* c, int32_t width, int32_t height, const rst_intrinsic
     level_geom(*intr, width, height, l, &c->geom[l]);
     c->pitch[l] = round_up(c->geom[l].w, 8);
     c->dframe[l] = (int64_t)c->pitch[l] * c->geom[l].h;
-    c->gframe[l] = (int64_t)c->geom[l].w * c->geom[l].h;
+    c->gframe[l] = (int64_t)c->geom[l].w * c->geom[l].h + kGeomGuard;  // guard texels in front of every frame
     c->chunks_per_row[l] = (c->geom[l].w + kChunkPx - 1) / kChunkPx;
     c->n_chunks[l] = c->chunks_per_row[l] * c->geom[l].h;
     // block extent depends on the image size only, so results never depend on the batch size
@@ -288,7 +291,10 @@ int32_t rst_begin(rst_ctx* c, int32_t width, int32_t height, const rst_intrinsic
   }
   if (!same || c->store_dirty) {
     // row padding (columns >= w) must read as invalid depth
-    for (int l = 0; l < RST_MAX_LEVELS; ++l) RST_CUDA(c, cudaMemsetAsync(c->d_depth[l], 0, c->depth_bytes[l], c->stream));
+    for (int l = 0; l < RST_MAX_LEVELS; ++l) {
+      RST_CUDA(c, cudaMemsetAsync(c->d_depth[l], 0, c->depth_bytes[l], c->stream));
+      RST_CUDA(c, cudaMemsetAsync(c->d_geom[l], 0, c->geom_bytes[l], c->stream));  // guard texels must read as invalid
+    }
     c->store_dirty = false;
   }
   c->ext0 = false; c->ext_depth0 = nullptr;
@@ -349,7 +355,7 @@ static LevelStore level_store(const rst_ctx* c, int l) {
   LevelStore s;
   if (l == 0 && c->ext0) { s.depth = c->ext_depth0; s.depth_pitch = c->ext_pitch0; s.depth_frame = c->ext_frame0; }
   else { s.depth = c->d_depth[l]; s.depth_pitch = c->pitch[l]; s.depth_frame = c->dframe[l]; }
-  s.geom = c->d_geom[l];
+  s.geom = c->d_geom[l] + kGeomGuard;
   s.geom_frame = c->gframe[l];
   return s;
 }
@@ -398,6 +404,8 @@ static void fill_icp_args(const rst_ctx* c, int l, IcpArgs* a) {
   a->chunks_per_row = c->chunks_per_row[l];
   a->n_chunks = c->n_chunks[l];
   a->groups = c->groups[l];
+  a->group_dv = kChunksPerBlock / c->chunks_per_row[l];
+  a->group_du = (kChunksPerBlock % c->chunks_per_row[l]) * kChunkPx;
   a->cpr_magic = (uint32_t)(((1ull << 32) + (uint64_t)c->chunks_per_row[l] - 1) / (uint64_t)c->chunks_per_row[l]);
   a->d_lo = c->d_lo; a->d_span = c->d_span;
   a->umax = (float)c->geom[l].w - 0.5f; a->vmax = (float)c->geom[l].h - 0.5f;
@@ -660,8 +668,8 @@ int32_t rst_read_geometry(rst_ctx* c, int32_t slot, int32_t level, float* out) {
   if (!c->begun || !out || level < 0 || level >= c->num_levels || slot < 0 || slot >= c->max_frames)
     return fail(c, RST_ERR_INVALID_ARG, "bad slot/level/out");
   RST_CUDA(c, cudaSetDevice(c->device));
-  const size_t n = (size_t)c->gframe[level];
-  RST_CUDA(c, cudaMemcpyAsync(out, c->d_geom[level] + (int64_t)slot * c->gframe[level], n * sizeof(float4),
+  const size_t n = (size_t)c->geom[level].w * c->geom[level].h;
+  RST_CUDA(c, cudaMemcpyAsync(out, c->d_geom[level] + kGeomGuard + (int64_t)slot * c->gframe[level], n * sizeof(float4),
                               cudaMemcpyDeviceToHost, c->stream));
   RST_CUDA(c, cudaStreamSynchronize(c->stream));
   return RST_OK;
@@ -683,7 +691,7 @@ int32_t rst_evaluate(rst_ctx* c, int32_t src_slot, int32_t dst_slot, int32_t lev
               c->d_stats + sp, c->d_tickets + sp, 1};
   RST_CUDA(c, launch_init_pairs(ia, c->stream));
   c->launches += 1;
-  const size_t npx = (size_t)c->gframe[level];
+  const size_t npx = (size_t)c->geom[level].w * c->geom[level].h;
   if (idx_out && c->idx_bytes < npx * 4) {
     cudaFree(c->d_idx); c->d_idx = nullptr; c->idx_bytes = 0;
     RST_CUDA(c, cudaMalloc(&c->d_idx, (size_t)c->max_w * c->max_h * 4));

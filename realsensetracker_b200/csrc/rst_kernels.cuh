@@ -30,10 +30,10 @@ constexpr int kAccPad = 32;       // partial row stride (floats)
 #define RST_ICP_THREADS 128
 #endif
 #ifndef RST_ICP_CPW
-#define RST_ICP_CPW 4
+#define RST_ICP_CPW 2
 #endif
 #ifndef RST_ICP_MINB
-#define RST_ICP_MINB 4
+#define RST_ICP_MINB 5
 #endif
 #ifndef RST_ICP_GROUP_PX
 #define RST_ICP_GROUP_PX 8192     // pixels per block on large levels (groups = this / block pixels per group)
@@ -41,6 +41,7 @@ constexpr int kAccPad = 32;       // partial row stride (floats)
 constexpr int kIcpThreads = RST_ICP_THREADS;
 constexpr int kChunkPx = 64;      // pixels one warp covers per step (2 per lane)
 constexpr int kChunksPerWarp = RST_ICP_CPW; // chunks per warp per group -> 2*CPW pixels in flight per thread
+constexpr int kPxPerStage = 2 * kChunksPerWarp;  // gathers per thread per pipeline stage
 constexpr float kMinProjZ = 1e-6f; // transformed points closer than this to the camera plane are rejected
 constexpr int kChunksPerBlock = (kIcpThreads / 32) * kChunksPerWarp;  // 32 -> 2048 px
 constexpr int kTileW = 64, kTileH = 32;  // preprocess tile
@@ -55,7 +56,7 @@ struct LevelStore {
   const uint16_t* depth;     // slot 0, row 0
   int32_t depth_pitch;       // pixels between rows
   int64_t depth_frame;       // pixels between frames
-  float4* geom;              // dense w*h per frame
+  float4* geom;              // dense w*h per frame; texel [-1] of every frame is an all-zero guard
   int64_t geom_frame;        // float4 between frames
 };
 
@@ -82,6 +83,7 @@ struct IcpArgs {
   int32_t max_blocks;
   int32_t blocks_per_pair, chunks_per_row, n_chunks;
   int32_t groups;             // groups of kChunksPerBlock chunks per block
+  int32_t group_dv, group_du; // kChunksPerBlock chunks = group_dv rows + group_du columns
   uint32_t cpr_magic;         // ceil(2^32 / chunks_per_row): c / chunks_per_row == umulhi(c, magic)
   uint32_t d_lo, d_span;      // valid raw depth: (d - d_lo) <= d_span  <=>  d != 0 && z_min <= d*scale <= z_max
   float umax, vmax;           // w - 0.5, h - 0.5
