@@ -159,9 +159,10 @@ void on_evaluate(const uint16_t* src_D, const float* src_G, const float* dst_G, 
       const float iz = 1.0f / qz_;
       const float uf = fmaf(L->fx, qx_ * iz, L->cx);
       const float vf = fmaf(L->fy, qy_ * iz, L->cy);
-      /* rint() of [-0.5, w-0.5) is always in [0, w-1]: -0.5 rounds to -0, w-0.5 is excluded */
-      if (!(uf >= -0.5f && uf < fw - 0.5f && vf >= -0.5f && vf < fh - 0.5f)) continue;
-      const int ui = (int)rintf(uf), vi = (int)rintf(vf);
+      /* accept iff the half-to-even rounded pixel lies in the image */
+      const float ur = rintf(uf), vr = rintf(vf);
+      if (!(ur >= 0.0f && ur <= fw - 1.0f && vr >= 0.0f && vr <= fh - 1.0f)) continue;
+      const int ui = (int)ur, vi = (int)vr;
       const float* g = dst_G + 4 * ((size_t)vi * w + ui);
       const float gz = g[3];
       if (!(gz > 0.0f)) continue;
