@@ -41,6 +41,7 @@ constexpr int kAccPad = 32;       // partial row stride (floats)
 constexpr int kIcpThreads = RST_ICP_THREADS;
 constexpr int kChunkPx = 64;      // pixels one warp covers per step (2 per lane)
 constexpr int kChunksPerWarp = RST_ICP_CPW; // chunks per warp per group -> 2*CPW pixels in flight per thread
+constexpr int kMaxGroups = RST_ICP_GROUP_PX / ((RST_ICP_THREADS / 32) * RST_ICP_CPW * 64);  // groups per block on large levels
 constexpr int kPxPerStage = 2 * kChunksPerWarp;  // gathers per thread per pipeline stage
 constexpr float kMinProjZ = 1e-6f; // transformed points closer than this to the camera plane are rejected
 constexpr int kChunksPerBlock = (kIcpThreads / 32) * kChunksPerWarp;  // 32 -> 2048 px
