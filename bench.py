@@ -321,7 +321,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         cpu = None
         if world == 1 and not args.no_cpu:
             cores = host_cores()
-            n_cpu = max(8, min(cores, n_pairs))
+            n_cpu = max(8, min(2 * cores, n_pairs))
             rate, dt, Tc, ok = cpu_reference_rate(frames, intr, n_cpu, cores)
             cerr = np.array([synth.pose_error(Tc[i], gt[i]) for i in range(n_cpu)])
             from oracle import oracle as O
@@ -341,7 +341,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "seq640x480_f2f_3level_icp (BASELINE.json configs[1])", "width": W, "height": H,
                        "frames_per_gpu_per_step": FRAMES, "pairs_per_gpu_per_step": n_pairs, "levels": 3,
-                       "iters_fine_to_coarse": list(ITERS), "accumulation": "fp32 per block (<=2048 px), fp64 across blocks and in the solve",
+                       "iters_fine_to_coarse": list(ITERS), "accumulation": "fp32 per block (<=8192 px), fp64 across blocks and in the solve",
                        "l2_policy": f"inputs larger than L2: {FRAMES * npx * (2 + 16) * 1.3125 / 1e6:.0f} MB of depth pyramid + geometry maps streamed per step (L2 = 126 MB)",
                        "parallelism": f"pairs sharded, {world} rank(s), NCCL all_gather of poses only"},
             "clocks": clocks,

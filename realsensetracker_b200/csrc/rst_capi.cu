@@ -275,7 +275,13 @@ int32_t rst_begin(rst_ctx* c, int32_t width, int32_t height, const rst_intrinsic
     c->chunks_per_row[l] = (c->geom[l].w + kChunkPx - 1) / kChunkPx;
     c->n_chunks[l] = c->chunks_per_row[l] * c->geom[l].h;
     // block extent depends on the image size only, so results never depend on the batch size
-    c->groups[l] = c->n_chunks[l] * kChunkPx >= 8 * RST_ICP_GROUP_PX ? RST_ICP_GROUP_PX / (kChunksPerBlock * kChunkPx) : 1;
+    {
+      // pixels per block ~ level size / 8, a power-of-two number of groups, at most kMaxGroups
+      const int group_px = kChunksPerBlock * kChunkPx;
+      int g = 1;
+      while (g * 2 <= kMaxGroups && (int64_t)g * 2 * group_px * 8 <= (int64_t)c->n_chunks[l] * kChunkPx) g *= 2;
+      c->groups[l] = g;
+    }
     const int cpb = kChunksPerBlock * c->groups[l];
     c->blocks_per_pair[l] = (c->n_chunks[l] + cpb - 1) / cpb;
   }
