@@ -163,6 +163,20 @@ int32_t rst_align_sequence(rst_ctx* ctx, const rst_frame* frames, int32_t n_fram
                            const rst_intrinsics* intr, const rst_params* params,
                            float* poses_inout, rst_stats* stats_out);
 
+/* Asynchronous forms: enqueue H2D, kernels and the D2H of the results into the context's pinned
+ * staging, and return without waiting; rst_wait() blocks until that work has finished and copies
+ * the poses (n x 16) / statistics (either may be NULL) out. `poses_in` may be NULL (identity
+ * priors). The host frames must stay valid until rst_wait returns. Two contexts driven
+ * alternately (submit k+1, wait k) overlap the PCIe copies of one batch with the kernels of the
+ * other — the streaming form of the odometry loop. One outstanding call per context. */
+int32_t rst_align_pairs_async(rst_ctx* ctx, const rst_frame* src, const rst_frame* dst,
+                              int32_t n_pairs, const rst_intrinsics* intr,
+                              const rst_params* params, const float* poses_in);
+int32_t rst_align_sequence_async(rst_ctx* ctx, const rst_frame* frames, int32_t n_frames,
+                                 const rst_intrinsics* intr, const rst_params* params,
+                                 const float* poses_in);
+int32_t rst_wait(rst_ctx* ctx, float* poses_out, rst_stats* stats_out);
+
 /* The two host-frame calls above upload and process their frames in chunks so that the
  * H2D copy of chunk k+1 (on an internal copy stream) overlaps the kernels of chunk k.
  * `frames_per_chunk` <= 0 disables the chunking (one upload, then one pass; the default).

@@ -60,7 +60,7 @@ ALIGN_SYMBOLS = [
     "rst_params_default", "rst_align_pairs", "rst_align_sequence", "rst_begin", "rst_upload_frames",
     "rst_set_frames_device", "rst_preprocess", "rst_align_slots", "rst_device_results", "rst_sync",
     "rst_level_info", "rst_read_depth", "rst_read_geometry", "rst_evaluate", "rst_launch_count",
-    "rst_copy_results_device", "rst_profile_enable", "rst_profile_read", "rst_set_pipeline_chunk",
+    "rst_copy_results_device", "rst_profile_enable", "rst_profile_read", "rst_set_pipeline_chunk", "rst_align_pairs_async", "rst_align_sequence_async", "rst_wait",
 ]
 
 _align = None
@@ -101,6 +101,12 @@ def align_lib() -> C.CDLL:
         lib.rst_align_sequence.argtypes = [C.c_void_p, P(Frame), C.c_int32, P(Intrinsics), P(Params),
                                            C.c_void_p, C.c_void_p]
         lib.rst_align_sequence.restype = C.c_int32
+        lib.rst_align_pairs_async.argtypes = [C.c_void_p, P(Frame), P(Frame), C.c_int32, P(Intrinsics), P(Params), C.c_void_p]
+        lib.rst_align_pairs_async.restype = C.c_int32
+        lib.rst_align_sequence_async.argtypes = [C.c_void_p, P(Frame), C.c_int32, P(Intrinsics), P(Params), C.c_void_p]
+        lib.rst_align_sequence_async.restype = C.c_int32
+        lib.rst_wait.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.rst_wait.restype = C.c_int32
         lib.rst_begin.argtypes = [C.c_void_p, C.c_int32, C.c_int32, P(Intrinsics), P(Params)]
         lib.rst_begin.restype = C.c_int32
         lib.rst_upload_frames.argtypes = [C.c_void_p, P(Frame), C.c_int32, C.c_int32]

@@ -109,6 +109,24 @@ class Aligner:
                                                  poses.ctypes.data, C.addressof(stats)))
         return cm_to_pose(poses), list(stats)
 
+    # ---- asynchronous form: submit now, wait later (two contexts ping-pong to overlap PCIe and kernels)
+    def submit_sequence(self, frames: np.ndarray, intr, params: Params | None = None):
+        """Enqueues upload + alignment + result download of a sequence and returns at once.
+        `frames` must stay alive (and unchanged) until wait() returns."""
+        P = params if params is not None else default_params()
+        K = Intrinsics(*intr)
+        self._pending = (frames.shape[0] - 1, _frames(frames), frames)
+        self._check(self._lib.rst_align_sequence_async(self._ctx, self._pending[1], frames.shape[0], C.byref(K), C.byref(P), None))
+
+    def wait(self):
+        """Blocks until the submitted work is done; returns (poses [n,4,4], list of Stats)."""
+        n = self._pending[0]
+        poses = np.empty((n, 16), dtype=np.float32)
+        stats = (Stats * n)()
+        self._check(self._lib.rst_wait(self._ctx, poses.ctypes.data, C.addressof(stats)))
+        self._pending = None
+        return cm_to_pose(poses), list(stats)
+
     # ---- staged API ---------------------------------------------------------------------------
     def begin(self, w: int, h: int, intr, params: Params):
         K = Intrinsics(*intr)

@@ -67,8 +67,10 @@ struct rst_ctx {
   rst_stats* h_stats = nullptr;
 
   cudaStream_t copy_stream = nullptr;   // H2D of the next chunk overlaps compute of the current one
+  cudaStream_t work_stream[2] = {nullptr, nullptr};  // chunks alternate between two compute streams
   int pipeline_chunk = 0;               // frames (pairs) per upload/compute chunk of the host entry points
   int n_pairs_last = 0;
+  int fetch_pending = 0;                // pairs whose results sit in the pinned staging of an *_async call
   int64_t launches = 0;
   std::string err;
 
@@ -171,6 +173,7 @@ void rst_ctx_destroy(rst_ctx* c) {
   for (auto& r : c->prof_open) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (int k = 0; k < 2; ++k) if (c->work_stream[k]) cudaStreamDestroy(c->work_stream[k]);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -217,6 +220,7 @@ int32_t rst_ctx_create(int32_t device, int32_t max_w, int32_t max_h, int32_t max
   if (stream) { c->stream = (cudaStream_t)stream; }
   else { CREATE_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   CREATE_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; ++k) CREATE_TRY(cudaStreamCreateWithFlags(&c->work_stream[k], cudaStreamNonBlocking));
   int w = max_w, h = max_h;
   for (int l = 0; l < RST_MAX_LEVELS; ++l) {
     const size_t px = (size_t)round_up(w, 8) * h;
@@ -475,17 +479,29 @@ static int32_t pairs_iterate(rst_ctx* c, int first, int n) {
   return RST_OK;
 }
 
-/* stage 3: results -> host (blocks until the stream has drained) */
+/* stage 3a: results -> pinned staging, asynchronously on the context stream */
+static int32_t fetch_enqueue(rst_ctx* c, int32_t n_pairs) {
+  RST_CUDA(c, cudaMemcpyAsync(c->h_poses, c->d_poses_cm, sizeof(float) * 16 * n_pairs, cudaMemcpyDeviceToHost, c->stream));
+  RST_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(rst_stats) * n_pairs, cudaMemcpyDeviceToHost, c->stream));
+  c->fetch_pending = n_pairs;
+  return RST_OK;
+}
+
+/* stage 3b: wait for the stream, hand the staged results to the caller */
+static int32_t fetch_finish(rst_ctx* c, float* poses_out, rst_stats* stats_out) {
+  RST_CUDA(c, cudaStreamSynchronize(c->stream));
+  const int n = c->fetch_pending;
+  c->fetch_pending = 0;
+  if (poses_out) std::memcpy(poses_out, c->h_poses, sizeof(float) * 16 * n);
+  if (stats_out) std::memcpy(stats_out, c->h_stats, sizeof(rst_stats) * n);
+  return RST_OK;
+}
+
 static int32_t pairs_fetch(rst_ctx* c, int32_t n_pairs, float* poses_out, rst_stats* stats_out) {
   if (!poses_out && !stats_out) return RST_OK;
-  if (poses_out)
-    RST_CUDA(c, cudaMemcpyAsync(c->h_poses, c->d_poses_cm, sizeof(float) * 16 * n_pairs, cudaMemcpyDeviceToHost, c->stream));
-  if (stats_out)
-    RST_CUDA(c, cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(rst_stats) * n_pairs, cudaMemcpyDeviceToHost, c->stream));
-  RST_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (poses_out) std::memcpy(poses_out, c->h_poses, sizeof(float) * 16 * n_pairs);
-  if (stats_out) std::memcpy(stats_out, c->h_stats, sizeof(rst_stats) * n_pairs);
-  return RST_OK;
+  int32_t rc = fetch_enqueue(c, n_pairs);
+  if (rc != RST_OK) return rc;
+  return fetch_finish(c, poses_out, stats_out);
 }
 
 int32_t rst_align_slots(rst_ctx* c, const int32_t* src_slots, const int32_t* dst_slots, int32_t n_pairs,
@@ -568,34 +584,31 @@ static int32_t check_frames(rst_ctx* c, const rst_frame* f, int n) {
   return RST_OK;
 }
 
-/* Uploads frames [f0, f1) on the copy stream and makes the compute stream wait for them. */
-static int32_t upload_chunk(rst_ctx* c, const rst_frame* frames, int n, int first_slot) {
-  cudaStream_t compute = c->stream;
-  c->stream = c->copy_stream;                       // rst_upload_frames copies on c->stream
-  const int32_t rc = rst_upload_frames(c, frames, n, first_slot);
-  c->stream = compute;
-  if (rc != RST_OK) return rc;
+/* ---- chunked host pipeline --------------------------------------------------------------------
+ * The frames of one call are cut into chunks. Chunk k is copied on the copy stream; its kernels run
+ * on work stream k % 2, so the H2D of chunk k+1 AND the latency-bound coarse-level launches of one
+ * chunk overlap the bandwidth-bound fine-level launches of the other (a single small chunk cannot
+ * fill 148 SMs). Results never depend on the chunking: every pair is reduced in blocks fixed by the
+ * image size. */
+struct StreamScope {  // kernels/copies issued through the ctx go to `s` while this object lives
+  rst_ctx* c; cudaStream_t saved;
+  StreamScope(rst_ctx* c_, cudaStream_t s) : c(c_), saved(c_->stream) { c->stream = s; }
+  ~StreamScope() { c->stream = saved; }
+};
+
+static int32_t link_streams(rst_ctx* c, cudaStream_t from, cudaStream_t to) {  // `to` waits for `from`
   cudaEvent_t e = prof_event(c);
-  RST_CUDA(c, cudaEventRecord(e, c->copy_stream));
-  RST_CUDA(c, cudaStreamWaitEvent(c->stream, e, 0));
-  c->ev_pool.push_back(e);                          // safe to recycle: the wait is already enqueued
+  RST_CUDA(c, cudaEventRecord(e, from));
+  RST_CUDA(c, cudaStreamWaitEvent(to, e, 0));
+  c->ev_pool.push_back(e);  // safe to recycle: the wait is already enqueued
   return RST_OK;
 }
 
-/* the copy stream must not overwrite frame slots that earlier compute work still reads */
-static int32_t copy_after_compute(rst_ctx* c) {
-  cudaEvent_t e = prof_event(c);
-  RST_CUDA(c, cudaEventRecord(e, c->stream));
-  RST_CUDA(c, cudaStreamWaitEvent(c->copy_stream, e, 0));
-  c->ev_pool.push_back(e);
-  return RST_OK;
-}
-
-int32_t rst_align_pairs(rst_ctx* c, const rst_frame* src, const rst_frame* dst, int32_t n_pairs,
-                        const rst_intrinsics* intr, const rst_params* params, float* poses_inout,
-                        rst_stats* stats_out) {
+static int32_t align_pairs_impl(rst_ctx* c, const rst_frame* src, const rst_frame* dst, int32_t n_pairs,
+                                const rst_intrinsics* intr, const rst_params* params, float* poses_inout,
+                                rst_stats* stats_out, bool wait) {
   if (!c) return RST_ERR_INVALID_ARG;
-  if (!src || !dst || n_pairs < 0 || !poses_inout) return fail(c, RST_ERR_INVALID_ARG, "null src/dst/poses or negative n_pairs");
+  if (!src || !dst || n_pairs < 0 || (wait && !poses_inout)) return fail(c, RST_ERR_INVALID_ARG, "null src/dst/poses or negative n_pairs");
   if (n_pairs == 0) return RST_OK;
   if (2 * (int64_t)n_pairs > c->max_frames || n_pairs > c->max_pairs) return fail(c, RST_ERR_CAPACITY, "batch exceeds the context capacity");
   int32_t rc;
@@ -605,25 +618,50 @@ int32_t rst_align_pairs(rst_ctx* c, const rst_frame* src, const rst_frame* dst, 
   std::vector<int32_t> s(n_pairs), d(n_pairs);
   for (int i = 0; i < n_pairs; ++i) { d[i] = i; s[i] = n_pairs + i; }
   if ((rc = pairs_begin(c, s.data(), d.data(), n_pairs, poses_inout)) != RST_OK) return rc;
-  if ((rc = copy_after_compute(c)) != RST_OK) return rc;
   const bool ngate = c->P.normal_cos_min > -1.0f;
-  // chunked so that the H2D copy of chunk k+1 overlaps pre-processing + ICP of chunk k
-  const int chunk = c->pipeline_chunk > 0 ? c->pipeline_chunk : n_pairs;
-  for (int p0 = 0; p0 < n_pairs; p0 += chunk) {
+  const int chunk = c->pipeline_chunk > 0 && c->pipeline_chunk < n_pairs ? c->pipeline_chunk : n_pairs;
+  const bool piped = chunk < n_pairs;
+  cudaStream_t main_s = c->stream;
+  if (piped) {
+    if ((rc = link_streams(c, main_s, c->copy_stream)) != RST_OK) return rc;
+    for (int k = 0; k < 2; ++k) if ((rc = link_streams(c, main_s, c->work_stream[k])) != RST_OK) return rc;
+  }
+  int ci = 0;
+  for (int p0 = 0; p0 < n_pairs; p0 += chunk, ++ci) {
     const int n = n_pairs - p0 < chunk ? n_pairs - p0 : chunk;
-    if ((rc = upload_chunk(c, dst + p0, n, p0)) != RST_OK) return rc;
-    if ((rc = upload_chunk(c, src + p0, n, n_pairs + p0)) != RST_OK) return rc;
+    cudaStream_t ws = piped ? c->work_stream[ci & 1] : main_s;
+    {
+      StreamScope up(c, piped ? c->copy_stream : main_s);
+      if ((rc = rst_upload_frames(c, dst + p0, n, p0)) != RST_OK) return rc;
+      if ((rc = rst_upload_frames(c, src + p0, n, n_pairs + p0)) != RST_OK) return rc;
+    }
+    if (piped && (rc = link_streams(c, c->copy_stream, ws)) != RST_OK) return rc;
+    StreamScope work(c, ws);
     if ((rc = preprocess_impl(c, p0, n, true)) != RST_OK) return rc;
     if ((rc = preprocess_impl(c, n_pairs + p0, n, ngate)) != RST_OK) return rc;
     if ((rc = pairs_iterate(c, p0, n)) != RST_OK) return rc;
   }
+  if (piped)
+    for (int k = 0; k < 2; ++k) if ((rc = link_streams(c, c->work_stream[k], main_s)) != RST_OK) return rc;
+  if (!wait) return fetch_enqueue(c, n_pairs);
   return pairs_fetch(c, n_pairs, poses_inout, stats_out);
 }
 
-int32_t rst_align_sequence(rst_ctx* c, const rst_frame* frames, int32_t n_frames, const rst_intrinsics* intr,
-                           const rst_params* params, float* poses_inout, rst_stats* stats_out) {
+int32_t rst_align_pairs(rst_ctx* c, const rst_frame* src, const rst_frame* dst, int32_t n_pairs,
+                        const rst_intrinsics* intr, const rst_params* params, float* poses_inout,
+                        rst_stats* stats_out) {
+  return align_pairs_impl(c, src, dst, n_pairs, intr, params, poses_inout, stats_out, true);
+}
+
+int32_t rst_align_pairs_async(rst_ctx* c, const rst_frame* src, const rst_frame* dst, int32_t n_pairs,
+                              const rst_intrinsics* intr, const rst_params* params, const float* poses_in) {
+  return align_pairs_impl(c, src, dst, n_pairs, intr, params, const_cast<float*>(poses_in), nullptr, false);
+}
+
+static int32_t align_sequence_impl(rst_ctx* c, const rst_frame* frames, int32_t n_frames, const rst_intrinsics* intr,
+                                   const rst_params* params, float* poses_inout, rst_stats* stats_out, bool wait) {
   if (!c) return RST_ERR_INVALID_ARG;
-  if (!frames || n_frames < 0 || !poses_inout) return fail(c, RST_ERR_INVALID_ARG, "null frames/poses or negative n_frames");
+  if (!frames || n_frames < 0 || (wait && !poses_inout)) return fail(c, RST_ERR_INVALID_ARG, "null frames/poses or negative n_frames");
   if (n_frames < 2) return RST_OK;
   if (n_frames > c->max_frames || n_frames - 1 > c->max_pairs) return fail(c, RST_ERR_CAPACITY, "sequence exceeds the context capacity");
   int32_t rc;
@@ -633,17 +671,50 @@ int32_t rst_align_sequence(rst_ctx* c, const rst_frame* frames, int32_t n_frames
   std::vector<int32_t> s(n_pairs), d(n_pairs);
   for (int i = 0; i < n_pairs; ++i) { s[i] = i + 1; d[i] = i; }  // AlignIcp3d(curr, prev): rs_replay_app.cpp:251
   if ((rc = pairs_begin(c, s.data(), d.data(), n_pairs, poses_inout)) != RST_OK) return rc;
-  if ((rc = copy_after_compute(c)) != RST_OK) return rc;
-  const int chunk = c->pipeline_chunk > 0 ? c->pipeline_chunk : n_frames;
-  for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+  const int chunk = c->pipeline_chunk > 0 && c->pipeline_chunk < n_frames ? c->pipeline_chunk : n_frames;
+  const bool piped = chunk < n_frames;
+  cudaStream_t main_s = c->stream;
+  if (piped) {
+    if ((rc = link_streams(c, main_s, c->copy_stream)) != RST_OK) return rc;
+    for (int k = 0; k < 2; ++k) if ((rc = link_streams(c, main_s, c->work_stream[k])) != RST_OK) return rc;
+  }
+  int ci = 0;
+  for (int f0 = 0; f0 < n_frames; f0 += chunk, ++ci) {
     const int n = n_frames - f0 < chunk ? n_frames - f0 : chunk;
-    if ((rc = upload_chunk(c, frames + f0, n, f0)) != RST_OK) return rc;
+    cudaStream_t ws = piped ? c->work_stream[ci & 1] : main_s;
+    {
+      StreamScope up(c, piped ? c->copy_stream : main_s);
+      if ((rc = rst_upload_frames(c, frames + f0, n, f0)) != RST_OK) return rc;
+    }
+    if (piped && (rc = link_streams(c, c->copy_stream, ws)) != RST_OK) return rc;
+    StreamScope work(c, ws);
     if ((rc = preprocess_impl(c, f0, n, true)) != RST_OK) return rc;
-    // pairs whose two frames are now resident: pair i uses frames i and i+1
+    // pair i uses frames i and i+1: the first pair of this chunk also needs the last frame of the previous
+    // chunk, pre-processed on the other work stream
     const int p0 = f0 > 0 ? f0 - 1 : 0, p1 = f0 + n - 1;
+    if (piped && ci > 0 && (rc = link_streams(c, c->work_stream[(ci - 1) & 1], ws)) != RST_OK) return rc;
     if ((rc = pairs_iterate(c, p0, p1 - p0)) != RST_OK) return rc;
   }
+  if (piped)
+    for (int k = 0; k < 2; ++k) if ((rc = link_streams(c, c->work_stream[k], main_s)) != RST_OK) return rc;
+  if (!wait) return fetch_enqueue(c, n_pairs);
   return pairs_fetch(c, n_pairs, poses_inout, stats_out);
+}
+
+int32_t rst_align_sequence(rst_ctx* c, const rst_frame* frames, int32_t n_frames, const rst_intrinsics* intr,
+                           const rst_params* params, float* poses_inout, rst_stats* stats_out) {
+  return align_sequence_impl(c, frames, n_frames, intr, params, poses_inout, stats_out, true);
+}
+
+int32_t rst_align_sequence_async(rst_ctx* c, const rst_frame* frames, int32_t n_frames, const rst_intrinsics* intr,
+                                 const rst_params* params, const float* poses_in) {
+  return align_sequence_impl(c, frames, n_frames, intr, params, const_cast<float*>(poses_in), nullptr, false);
+}
+
+int32_t rst_wait(rst_ctx* c, float* poses_out, rst_stats* stats_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  RST_CUDA(c, cudaSetDevice(c->device));
+  return fetch_finish(c, poses_out, stats_out);
 }
 
 int32_t rst_level_info(const rst_ctx* c, int32_t level, int32_t* width, int32_t* height, int32_t* pitch_px,

@@ -261,3 +261,27 @@ def test_capacity_and_argument_errors():
         assert "INVALID_ARG" in str(e.value)
     finally:
         al.close()
+
+
+def test_async_submit_wait_equals_blocking_call(seq640):
+    """Two contexts driven alternately (the streaming form): same bits as the blocking call."""
+    frames, gt, intr = seq640
+    P, _ = both_params()
+    a, b = Aligner(640, 480, 8, 4), Aligner(640, 480, 5, 4)
+    try:
+        Tref, sref = a.align_sequence(frames, intr, P)
+        a.submit_sequence(frames, intr, P)
+        b.submit_sequence(frames[::-1].copy(), intr, P)
+        Ta, sa = a.wait()
+        Tb, sb = b.wait()
+        assert np.array_equal(Ta, Tref) and [s.count for s in sa] == [s.count for s in sref]
+        Trev, _ = a.align_sequence(frames[::-1].copy(), intr, P)
+        assert np.array_equal(Tb, Trev)
+        for chunk in (2, 3):      # chunked two-stream pipeline inside one call: same bits
+            a.set_pipeline_chunk(chunk)
+            Tc, _ = a.align_sequence(frames, intr, P)
+            assert np.array_equal(Tc, Tref)
+            Tp, _ = a.align_pairs(frames[1:], frames[:-1], intr, P)
+            assert np.array_equal(Tp, Tref)
+    finally:
+        a.close(); b.close()
