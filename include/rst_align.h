@@ -249,6 +249,41 @@ int32_t rst_evaluate(rst_ctx* ctx, int32_t src_slot, int32_t dst_slot,
                      int32_t level, const float* pose, int32_t* idx_out,
                      rst_stats* stats_out);
 
+/* -------------------------------------------------------------------------
+ * Cloud-based alignment with the reference's own algorithm, on the GPU.
+ * Literal counterpart of
+ *   bool AlignIcp3d(const Cloud3f& src, const Cloud3f& dst, const int max_iter,
+ *                   Eigen::Isometry3f* const transform)   align_icp.cpp:73-167
+ * exact 1-NN of every transformed source point in dst (kdtree.hpp:51-57, here a uniform
+ * grid with ring expansion — exact, ties to the lowest index), Geman-McClure weights with mu
+ * annealed /1.4 every 8 iterations (:91,96-98,116-118), UNWEIGHTED dst/src centroids
+ * (:85-86,120-122), weighted fp32-product / fp64-accumulated cross-covariance (:125-136),
+ * 3x3 SVD -> R = U V^T with the literal reflection patch (:139-145), t = mu_d - R mu_s (:148),
+ * Translation * Quaternion round trip (:151), fixed max_iter iterations, returns
+ * mean_cost = sqrt(cost/N) of the last iteration's pre-update correspondences (:157-160).
+ * Clouds are xyz-interleaved fp32 (the memory of Cloud3f = Eigen 3xN column-major), HOST pointers.
+ * ---------------------------------------------------------------------- */
+typedef struct rst_cloud {
+  const float* xyz;  /* n x 3 */
+  int32_t n;
+} rst_cloud;
+
+typedef struct rst_icp3d_result {
+  int32_t ok;        /* the reference's return value: n >= 3 && m >= 3 && mean_cost < 10000 */
+  int32_t iterations;
+  float mean_cost;   /* sqrt(sum d^2 / N), last iteration, pre-update                       */
+  float mu;          /* final Geman-McClure mu                                              */
+  double cov[9];     /* last iteration's cross-covariance, row-major                        */
+} rst_icp3d_result;
+
+/* pair i aligns src[i] onto dst[i]; poses_inout: n_pairs x 16 column-major fp32, initial guess in,
+ * result out. results / nbrs_out / weights_out may be NULL; nbrs_out and weights_out receive the
+ * last iteration's correspondences of all pairs back to back (sum of src[i].n entries).
+ * grid_cell <= 0 picks the search-grid cell size automatically. */
+int32_t rst_icp3d_pairs(rst_ctx* ctx, const rst_cloud* src, const rst_cloud* dst, int32_t n_pairs,
+                        int32_t max_iter, float grid_cell, float* poses_inout,
+                        rst_icp3d_result* results, int32_t* nbrs_out, float* weights_out);
+
 /* Number of kernel launches this context has issued so far (bench evidence). */
 int64_t rst_launch_count(const rst_ctx* ctx);
 

@@ -48,6 +48,15 @@ class Stats(C.Structure):
                 ("sum_wr2", C.c_double), ("A", C.c_double * 21), ("b", C.c_double * 6)]
 
 
+class Cloud(C.Structure):
+    _fields_ = [("xyz", C.c_void_p), ("n", C.c_int32)]
+
+
+class Icp3dResult(C.Structure):
+    _fields_ = [("ok", C.c_int32), ("iterations", C.c_int32), ("mean_cost", C.c_float), ("mu", C.c_float),
+                ("cov", C.c_double * 9)]
+
+
 class Profile(C.Structure):
     _fields_ = [("ms_preprocess", C.c_float * RST_MAX_LEVELS), ("ms_icp", C.c_float * RST_MAX_LEVELS),
                 ("launches_preprocess", C.c_int32 * RST_MAX_LEVELS), ("launches_icp", C.c_int32 * RST_MAX_LEVELS),
@@ -60,7 +69,7 @@ ALIGN_SYMBOLS = [
     "rst_params_default", "rst_align_pairs", "rst_align_sequence", "rst_begin", "rst_upload_frames",
     "rst_set_frames_device", "rst_preprocess", "rst_align_slots", "rst_device_results", "rst_sync",
     "rst_level_info", "rst_read_depth", "rst_read_geometry", "rst_evaluate", "rst_launch_count",
-    "rst_copy_results_device", "rst_profile_enable", "rst_profile_read", "rst_set_pipeline_chunk", "rst_align_pairs_async", "rst_align_sequence_async", "rst_wait",
+    "rst_copy_results_device", "rst_profile_enable", "rst_profile_read", "rst_set_pipeline_chunk", "rst_align_pairs_async", "rst_align_sequence_async", "rst_wait", "rst_icp3d_pairs",
 ]
 
 _align = None
@@ -107,6 +116,9 @@ def align_lib() -> C.CDLL:
         lib.rst_align_sequence_async.restype = C.c_int32
         lib.rst_wait.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.rst_wait.restype = C.c_int32
+        lib.rst_icp3d_pairs.argtypes = [C.c_void_p, P(Cloud), P(Cloud), C.c_int32, C.c_int32, C.c_float, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.rst_icp3d_pairs.restype = C.c_int32
         lib.rst_begin.argtypes = [C.c_void_p, C.c_int32, C.c_int32, P(Intrinsics), P(Params)]
         lib.rst_begin.restype = C.c_int32
         lib.rst_upload_frames.argtypes = [C.c_void_p, P(Frame), C.c_int32, C.c_int32]

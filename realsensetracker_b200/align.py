@@ -127,6 +127,36 @@ class Aligner:
         self._pending = None
         return cm_to_pose(poses), list(stats)
 
+    # ---- cloud-based alignment with the reference's own algorithm (AlignIcp3d, align_icp.cpp:73-167)
+    def icp3d_pairs(self, src_clouds, dst_clouds, max_iter: int = 128, T0=None, grid_cell: float = 0.1, details: bool = False):
+        """src_clouds/dst_clouds: lists of [n,3] float32 arrays. Returns (ok [n] bool, poses [n,4,4])
+        and, with details=True, a list of dicts (mean_cost, cov, nbrs, weights of the last iteration)."""
+        n = len(src_clouds)
+        S = [np.ascontiguousarray(a, dtype=np.float32) for a in src_clouds]
+        D = [np.ascontiguousarray(a, dtype=np.float32) for a in dst_clouds]
+        cs, cd = (N.Cloud * n)(), (N.Cloud * n)()
+        for i in range(n):
+            cs[i].xyz, cs[i].n = S[i].ctypes.data, len(S[i])
+            cd[i].xyz, cd[i].n = D[i].ctypes.data, len(D[i])
+        poses = pose_to_cm(np.broadcast_to(np.eye(4) if T0 is None else T0, (n, 4, 4))).copy()
+        res = (N.Icp3dResult * n)()
+        tot = sum(len(a) for a in S)
+        nbrs = np.empty(tot, dtype=np.int32) if details else None
+        wts = np.empty(tot, dtype=np.float32) if details else None
+        self._check(self._lib.rst_icp3d_pairs(self._ctx, cs, cd, n, max_iter, grid_cell, poses.ctypes.data, C.addressof(res),
+                                              nbrs.ctypes.data if details else None, wts.ctypes.data if details else None))
+        ok = np.array([r.ok != 0 for r in res])
+        T = cm_to_pose(poses)
+        if not details:
+            return ok, T
+        out, o = [], 0
+        for i in range(n):
+            m = len(S[i])
+            out.append(dict(mean_cost=res[i].mean_cost, mu=res[i].mu, cov=np.array(res[i].cov[:]).reshape(3, 3),
+                            nbrs=nbrs[o:o + m].copy(), weights=wts[o:o + m].copy()))
+            o += m
+        return ok, T, out
+
     # ---- staged API ---------------------------------------------------------------------------
     def begin(self, w: int, h: int, intr, params: Params):
         K = Intrinsics(*intr)
@@ -207,6 +237,19 @@ class Aligner:
     @property
     def launch_count(self) -> int:
         return int(self._lib.rst_launch_count(self._ctx))
+
+
+def AlignIcp3d(src: np.ndarray, dst: np.ndarray, max_iter: int = 128, transform=None, aligner: Aligner | None = None):
+    """The reference's signature on the GPU: bool AlignIcp3d(src, dst, max_iter, &transform)
+    (align_icp.hpp:22-24). Returns (success, transform 4x4)."""
+    own = aligner is None
+    al = aligner or Aligner(16, 16, 2, 1)
+    try:
+        ok, T = al.icp3d_pairs([src], [dst], max_iter, T0=transform)
+    finally:
+        if own:
+            al.close()
+    return bool(ok[0]), T[0]
 
 
 def AlignRgbd(src_depth: np.ndarray, dst_depth: np.ndarray, K, params: Params | None = None, transform=None,

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "rst_align.h"
+#include "rst_internal.h"
 #include "rst_kernels.cuh"
 
 using namespace rst;
@@ -69,6 +70,8 @@ struct rst_ctx {
   cudaStream_t copy_stream = nullptr;   // H2D of the next chunk overlaps compute of the current one
   cudaStream_t work_stream[2] = {nullptr, nullptr};  // chunks alternate between two compute streams
   int pipeline_chunk = 0;               // frames (pairs) per upload/compute chunk of the host entry points
+  void* ext = nullptr;                  // state of the cloud-based engine (rst_icp3d.cu), created on first use
+  void (*ext_free)(void*) = nullptr;
   int n_pairs_last = 0;
   int fetch_pending = 0;                // pairs whose results sit in the pinned staging of an *_async call
   int64_t launches = 0;
@@ -104,6 +107,14 @@ static void prof_end(rst_ctx* c, int h, int launches, int64_t units) {
 }
 
 static thread_local std::string g_create_err;
+
+namespace rst {
+cudaStream_t ctx_stream(rst_ctx* c) { return c->stream; }
+int ctx_device(rst_ctx* c) { return c->device; }
+void ctx_set_error(rst_ctx* c, const std::string& msg) { c->err = msg; }
+void ctx_count_launches(rst_ctx* c, int n) { c->launches += n; }
+void** ctx_ext_slot(rst_ctx* c, void (***free_fn)(void*)) { *free_fn = &c->ext_free; return &c->ext; }
+}  // namespace rst
 
 #define RST_CUDA(ctx, expr)                                                              \
   do {                                                                                   \
@@ -165,6 +176,7 @@ void rst_ctx_destroy(rst_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->ext && c->ext_free) c->ext_free(c->ext);
   for (int l = 0; l < RST_MAX_LEVELS; ++l) { cudaFree(c->d_depth[l]); cudaFree(c->d_geom[l]); }
   cudaFree(c->d_pairs); cudaFree(c->d_poses_in); cudaFree(c->d_master); cudaFree(c->d_pose_f32);
   cudaFree(c->d_poses_cm); cudaFree(c->d_stats); cudaFree(c->d_tickets); cudaFree(c->d_partials);

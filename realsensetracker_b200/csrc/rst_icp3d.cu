@@ -1,0 +1,484 @@
+/*
+ * rst_icp3d.cu — the reference's own cloud-based ICP on the GPU.
+ *
+ * Literal counterpart of AlignIcp3d (rs_tracker/align/src/align_icp.cpp:73-167): exact nearest
+ * neighbour + Geman-McClure/GNC weights + weighted cross-covariance + 3x3 SVD (Kabsch) + quaternion
+ * round trip, max_iter fixed iterations. One thread block of 1024 threads owns one pair and runs ALL
+ * iterations inside one launch (the pose lives in shared memory, phases are separated by
+ * __syncthreads), so a batch of pairs is one kernel launch and there is no host round trip per
+ * iteration. The KD-tree (nanoflann, kdtree.hpp:27-57) is replaced by a uniform grid over the dst
+ * cloud built in the same kernel, searched in growing rings until the ring bound proves the current
+ * best is the exact nearest neighbour (ties: lowest index).
+ *
+ * fp32 arithmetic that decides a neighbour (transform, squared distance) uses explicit
+ * round-to-nearest intrinsics in the reference's operation order (no FMA contraction), so NN indices
+ * and weights are bit-identical to the CPU restatement for the same input pose.
+ */
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rst_align.h"
+#include "rst_internal.h"
+
+namespace {
+
+constexpr int kThreads = 1024;
+constexpr int kWarps = kThreads / 32;
+constexpr int kCellCap = 1 << 18;  // grid cells per pair (1 MiB of cell_start)
+
+struct PairDesc {
+  const float* src;   // n x 3
+  const float* dst;   // m x 3
+  int n, m;
+  int* cell_start;    // [kCellCap + 1]
+  int* cell_fill;     // [kCellCap]
+  float4* sorted;     // m: x, y, z, original index (bit pattern)
+  int* nbr;           // n
+  float* w;           // n
+  float* pose;        // 16, column-major, in/out
+  rst_icp3d_result* res;
+};
+
+struct Grid {
+  float lox, loy, loz, h, inv_h;
+  int nx, ny, nz;
+};
+
+__device__ __forceinline__ float mulrn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float addrn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float subrn(float a, float b) { return __fsub_rn(a, b); }
+
+// block-wide sum of K doubles, fixed order (xor tree inside a warp, warps in index order)
+template <int K>
+__device__ void block_sum(double (&v)[K], double (*s_part)[16], double* s_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double x = v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) s_part[warp][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double x = 0.0;
+    for (int w = 0; w < kWarps; ++w) x += s_part[w][threadIdx.x];
+    s_out[threadIdx.x] = x;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int cell_coord(float p, float lo, float inv_h, int n) {
+  int c = (int)floorf((p - lo) * inv_h);
+  return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+
+// exact nearest neighbour of p in the gridded dst cloud; ties go to the lowest original index
+__device__ void nn_search(const Grid& g, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
+                          float px, float py, float pz, int* best_j, float* best_d2) {
+  const int cx = cell_coord(px, g.lox, g.inv_h, g.nx), cy = cell_coord(py, g.loy, g.inv_h, g.ny),
+            cz = cell_coord(pz, g.loz, g.inv_h, g.nz);
+  float bd = FLT_MAX;
+  int bj = 0x7fffffff;
+  for (int r = 0;; ++r) {
+    const int x0 = max(cx - r, 0), x1 = min(cx + r, g.nx - 1);
+    const int y0 = max(cy - r, 0), y1 = min(cy + r, g.ny - 1);
+    const int z0 = max(cz - r, 0), z1 = min(cz + r, g.nz - 1);
+    for (int z = z0; z <= z1; ++z)
+      for (int y = y0; y <= y1; ++y) {
+        const bool inner_zy = (abs(z - cz) < r) && (abs(y - cy) < r);
+        for (int x = x0; x <= x1; ++x) {
+          if (inner_zy && abs(x - cx) < r) { x = cx + r - 1; continue; }  // interior was visited by smaller rings
+          const int c = (z * g.ny + y) * g.nx + x;
+          const int e = cell_start[c + 1];
+          for (int k = cell_start[c]; k < e; ++k) {
+            const float4 q = sorted[k];
+            const float dx = subrn(px, q.x), dy = subrn(py, q.y), dz = subrn(pz, q.z);
+            const float d2 = addrn(addrn(mulrn(dx, dx), mulrn(dy, dy)), mulrn(dz, dz));  // left to right, as nanoflann L2
+            const int j = __float_as_int(q.w);
+            if (d2 < bd || (d2 == bd && j < bj)) { bd = d2; bj = j; }
+          }
+        }
+      }
+    if (x0 == 0 && x1 == g.nx - 1 && y0 == 0 && y1 == g.ny - 1 && z0 == 0 && z1 == g.nz - 1) break;  // whole grid seen
+    // every unvisited point lies beyond one of the (unclipped) faces of the visited box
+    float bound = FLT_MAX;
+    if (cx - r > 0) bound = fminf(bound, px - (g.lox + (float)(cx - r) * g.h));
+    if (cx + r < g.nx - 1) bound = fminf(bound, (g.lox + (float)(cx + r + 1) * g.h) - px);
+    if (cy - r > 0) bound = fminf(bound, py - (g.loy + (float)(cy - r) * g.h));
+    if (cy + r < g.ny - 1) bound = fminf(bound, (g.loy + (float)(cy + r + 1) * g.h) - py);
+    if (cz - r > 0) bound = fminf(bound, pz - (g.loz + (float)(cz - r) * g.h));
+    if (cz + r < g.nz - 1) bound = fminf(bound, (g.loz + (float)(cz + r + 1) * g.h) - pz);
+    bound -= 1e-3f * g.h;  // slack for the rounding of the point -> cell assignment
+    if (bound > 0.0f && bd <= bound * bound * 0.9999f) break;
+  }
+  *best_j = bj;
+  *best_d2 = bd;
+}
+
+// R = U V^T of a 3x3 fp64 matrix by one-sided Jacobi (row-major in/out)
+__device__ void svd_uvt(const double* M, double* UVt) {
+  double B[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int i = 0; i < 9; ++i) B[i] = M[i];
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double a = 0, b = 0, c = 0;
+        for (int i = 0; i < 3; ++i) { a += B[3 * i + p] * B[3 * i + p]; b += B[3 * i + q] * B[3 * i + q]; c += B[3 * i + p] * B[3 * i + q]; }
+        off = fmax(off, fabs(c) / sqrt(a * b + 1e-300));
+        if (fabs(c) <= 1e-300) continue;
+        const double zeta = (b - a) / (2.0 * c);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+        for (int i = 0; i < 3; ++i) {
+          const double bp = B[3 * i + p], bq = B[3 * i + q];
+          B[3 * i + p] = cs * bp - sn * bq; B[3 * i + q] = sn * bp + cs * bq;
+          const double vp = V[3 * i + p], vq = V[3 * i + q];
+          V[3 * i + p] = cs * vp - sn * vq; V[3 * i + q] = sn * vp + cs * vq;
+        }
+      }
+    if (off < 1e-15) break;
+  }
+  double U[9], s[3];
+  for (int j = 0; j < 3; ++j) s[j] = sqrt(B[j] * B[j] + B[3 + j] * B[3 + j] + B[6 + j] * B[6 + j]);
+  const double smax = fmax(s[0], fmax(s[1], s[2]));
+  int bad = -1;
+  for (int j = 0; j < 3; ++j) {
+    if (s[j] > 1e-14 * smax && s[j] > 0) { for (int i = 0; i < 3; ++i) U[3 * i + j] = B[3 * i + j] / s[j]; }
+    else bad = j;
+  }
+  if (bad >= 0) {  // rank-deficient covariance: complete the basis with the cross product
+    const int a = (bad + 1) % 3, b = (bad + 2) % 3;
+    U[bad] = U[3 + a] * U[6 + b] - U[6 + a] * U[3 + b];
+    U[3 + bad] = U[6 + a] * U[b] - U[a] * U[6 + b];
+    U[6 + bad] = U[a] * U[3 + b] - U[3 + a] * U[b];
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double acc = 0;
+      for (int k = 0; k < 3; ++k) acc += U[3 * i + k] * V[3 * j + k];
+      UVt[3 * i + j] = acc;
+    }
+}
+
+// xfm = Translation3f{t} * Quaternionf{R} (align_icp.cpp:151), column-major 4x4 out
+__device__ void compose_pose(const float* R, const float* t, float* T) {
+  float q[4];  // x y z w
+  float tr = R[0] + R[4] + R[8];
+  if (tr > 0.f) {
+    tr = sqrtf(tr + 1.0f);
+    q[3] = 0.5f * tr;
+    tr = 0.5f / tr;
+    q[0] = (R[7] - R[5]) * tr; q[1] = (R[2] - R[6]) * tr; q[2] = (R[3] - R[1]) * tr;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    tr = sqrtf(R[4 * i] - R[4 * j] - R[4 * k] + 1.0f);
+    q[i] = 0.5f * tr;
+    tr = 0.5f / tr;
+    q[3] = (R[3 * k + j] - R[3 * j + k]) * tr;
+    q[j] = (R[3 * j + i] + R[3 * i + j]) * tr;
+    q[k] = (R[3 * k + i] + R[3 * i + k]) * tr;
+  }
+  const float tx = 2.f * q[0], ty = 2.f * q[1], tz = 2.f * q[2];
+  const float twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
+  const float txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+  const float tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+  const float Rq[9] = {1.f - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1.f - (txx + tzz), tyz - twx,
+                       txz - twy, tyz + twx, 1.f - (txx + tyy)};
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) T[r + 4 * c] = Rq[3 * r + c];
+    T[12 + r] = t[r];
+    T[4 * r + 3] = 0.f;
+  }
+  T[15] = 1.f;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restrict__ descs, int max_iter, float grid_cell) {
+  __shared__ double s_part[kWarps][16];
+  __shared__ double s_sum[16];
+  __shared__ float s_T[16];
+  __shared__ float s_box[6];
+  __shared__ int s_scan[kWarps];
+  __shared__ Grid s_grid;
+
+  const PairDesc P = descs[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (P.n < 3 || P.m < 3) {  // align_icp.cpp:77-79: false, pose untouched
+    if (tid == 0 && P.res) { rst_icp3d_result r{}; *P.res = r; }
+    return;
+  }
+
+  // ---- uniform grid over dst: bounding box
+  {
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int j = tid; j < P.m; j += kThreads)
+      for (int a = 0; a < 3; ++a) { const float v = P.dst[3 * j + a]; lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+    for (int a = 0; a < 3; ++a)
+      for (int o = 16; o > 0; o >>= 1) {
+        lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+        hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+      }
+    float* s_f = reinterpret_cast<float*>(&s_part[0][0]);  // [warp][6]
+    if (lane == 0) for (int a = 0; a < 3; ++a) { s_f[warp * 6 + a] = lo[a]; s_f[warp * 6 + 3 + a] = hi[a]; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int a = 0; a < 3; ++a) {
+        float l = FLT_MAX, h = -FLT_MAX;
+        for (int w = 0; w < kWarps; ++w) { l = fminf(l, s_f[w * 6 + a]); h = fmaxf(h, s_f[w * 6 + 3 + a]); }
+        s_box[a] = l; s_box[3 + a] = h;
+      }
+      Grid g;
+      g.lox = s_box[0]; g.loy = s_box[1]; g.loz = s_box[2];
+      const float ex = s_box[3] - s_box[0], ey = s_box[4] - s_box[1], ez = s_box[5] - s_box[2];
+      float h = grid_cell > 0.f ? grid_cell : fmaxf(fmaxf(ex, fmaxf(ey, ez)) / 64.f, 1e-6f);
+      for (;;) {
+        g.nx = (int)floorf(ex / h) + 1; g.ny = (int)floorf(ey / h) + 1; g.nz = (int)floorf(ez / h) + 1;
+        if ((long long)g.nx * g.ny * g.nz <= kCellCap) break;
+        h *= 1.26f;
+      }
+      g.h = h; g.inv_h = 1.0f / h;
+      s_grid = g;
+    }
+    __syncthreads();
+  }
+  const Grid g = s_grid;
+  const int n_cells = g.nx * g.ny * g.nz;
+
+  // ---- counting sort of dst into cells
+  for (int c = tid; c < n_cells; c += kThreads) P.cell_fill[c] = 0;
+  __syncthreads();
+  for (int j = tid; j < P.m; j += kThreads) {
+    const int c = (cell_coord(P.dst[3 * j + 2], g.loz, g.inv_h, g.nz) * g.ny + cell_coord(P.dst[3 * j + 1], g.loy, g.inv_h, g.ny)) * g.nx +
+                  cell_coord(P.dst[3 * j], g.lox, g.inv_h, g.nx);
+    atomicAdd(P.cell_fill + c, 1);
+  }
+  __syncthreads();
+  {
+    const int per = (n_cells + kThreads - 1) / kThreads;
+    const int c0 = tid * per, c1 = min(c0 + per, n_cells);
+    int local = 0;
+    for (int c = c0; c < c1; ++c) local += P.cell_fill[c];
+    int incl = local;  // inclusive scan of the per-thread totals
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int v = s_scan[lane];
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+      s_scan[lane] = v;
+    }
+    __syncthreads();
+    int run = incl - local + (warp > 0 ? s_scan[warp - 1] : 0);
+    for (int c = c0; c < c1; ++c) { const int k = P.cell_fill[c]; P.cell_start[c] = run; P.cell_fill[c] = 0; run += k; }
+    if (tid == 0) P.cell_start[n_cells] = P.m;
+  }
+  __syncthreads();
+  for (int j = tid; j < P.m; j += kThreads) {
+    const float x = P.dst[3 * j], y = P.dst[3 * j + 1], z = P.dst[3 * j + 2];
+    const int c = (cell_coord(z, g.loz, g.inv_h, g.nz) * g.ny + cell_coord(y, g.loy, g.inv_h, g.ny)) * g.nx + cell_coord(x, g.lox, g.inv_h, g.nx);
+    const int pos = P.cell_start[c] + atomicAdd(P.cell_fill + c, 1);
+    P.sorted[pos] = make_float4(x, y, z, __int_as_float(j));
+  }
+  __syncthreads();
+
+  // ---- src centroid (ComputeCentroid, point_cloud_utils.cpp:92-98), pose -> shared
+  float smean[3];
+  {
+    double acc[3] = {0, 0, 0};
+    for (int i = tid; i < P.n; i += kThreads)
+      for (int a = 0; a < 3; ++a) acc[a] += (double)P.src[3 * i + a];
+    block_sum<3>(acc, s_part, s_sum);
+    const float inv = (float)(1.0 / (double)P.n);
+    for (int a = 0; a < 3; ++a) smean[a] = (float)s_sum[a] * inv;
+  }
+  if (tid < 16) s_T[tid] = P.pose[tid];
+  __syncthreads();
+
+  float mu = 1.0f;  // align_icp.cpp:91
+  double cost = 0.0;
+  for (int iter = 0; iter < max_iter; ++iter) {
+    if (iter > 0 && iter % 8 == 0) mu = __fdiv_rn(mu, 1.4f);  // :96-98
+    float T[12];
+    T[0] = s_T[0]; T[1] = s_T[1]; T[2] = s_T[2]; T[3] = s_T[4]; T[4] = s_T[5]; T[5] = s_T[6];
+    T[6] = s_T[8]; T[7] = s_T[9]; T[8] = s_T[10]; T[9] = s_T[12]; T[10] = s_T[13]; T[11] = s_T[14];
+    // ---- correspondences + weights (:105-121)
+    double a4[4] = {0, 0, 0, 0};  // cost, sum dst_j
+    for (int i = tid; i < P.n; i += kThreads) {
+      const float sx = P.src[3 * i], sy = P.src[3 * i + 1], sz = P.src[3 * i + 2];
+      // Isometry3f * Vector3f, left to right, no contraction
+      const float px = addrn(addrn(addrn(mulrn(T[0], sx), mulrn(T[3], sy)), mulrn(T[6], sz)), T[9]);
+      const float py = addrn(addrn(addrn(mulrn(T[1], sx), mulrn(T[4], sy)), mulrn(T[7], sz)), T[10]);
+      const float pz = addrn(addrn(addrn(mulrn(T[2], sx), mulrn(T[5], sy)), mulrn(T[8], sz)), T[11]);
+      int j; float d2;
+      nn_search(g, P.cell_start, P.sorted, px, py, pz, &j, &d2);
+      const float rt = __fdiv_rn(mu, addrn(d2, mu));
+      P.nbr[i] = j;
+      P.w[i] = mulrn(rt, rt);
+      a4[0] += (double)d2;
+      a4[1] += (double)P.dst[3 * j]; a4[2] += (double)P.dst[3 * j + 1]; a4[3] += (double)P.dst[3 * j + 2];
+    }
+    block_sum<4>(a4, s_part, s_sum);
+    cost = s_sum[0];
+    float dmean[3];
+    for (int a = 0; a < 3; ++a) dmean[a] = (float)s_sum[1 + a] / (float)P.n;  // :122, unweighted
+    // ---- weighted cross-covariance: fp32 products, fp64 accumulation (:125-136)
+    double cv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = tid; i < P.n; i += kThreads) {
+      const int j = P.nbr[i];
+      const float w = P.w[i];
+      float ds[3], wd[3];
+      for (int a = 0; a < 3; ++a) {
+        wd[a] = mulrn(w, subrn(P.dst[3 * j + a], dmean[a]));
+        ds[a] = subrn(P.src[3 * i + a], smean[a]);
+      }
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) cv[3 * a + b] += (double)mulrn(wd[a], ds[b]);
+    }
+    block_sum<9>(cv, s_part, s_sum);
+    // ---- closed-form pose (:139-151)
+    if (tid == 0) {
+      double cov[9], uvt[9];
+      for (int k = 0; k < 9; ++k) cov[k] = s_sum[k];
+      svd_uvt(cov, uvt);
+      float R[9], t[3];
+      for (int k = 0; k < 9; ++k) R[k] = (float)uvt[k];
+      const float det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+      if (det < 0) { R[2] *= -1; R[5] *= -1; R[8] *= -1; }  // R.col(2) *= -1, as written (:143-145)
+      for (int a = 0; a < 3; ++a) t[a] = dmean[a] - (R[3 * a] * smean[0] + R[3 * a + 1] * smean[1] + R[3 * a + 2] * smean[2]);
+      float Tn[16];
+      compose_pose(R, t, Tn);
+      for (int k = 0; k < 16; ++k) s_T[k] = Tn[k];
+      if (P.res && iter == max_iter - 1) for (int k = 0; k < 9; ++k) P.res->cov[k] = cov[k];
+    }
+    __syncthreads();
+  }
+  if (tid < 16) P.pose[tid] = s_T[tid];  // :156
+  if (tid == 0 && P.res) {
+    const float mean_cost = sqrtf((float)cost / (float)P.n);  // :157
+    P.res->mean_cost = mean_cost;
+    P.res->ok = mean_cost < 10000.f ? 1 : 0;                  // :160
+    P.res->iterations = max_iter;
+    P.res->mu = mu;
+    if (max_iter == 0) for (int k = 0; k < 9; ++k) P.res->cov[k] = 0.0;
+  }
+}
+
+/* grow-only device/pinned arenas of the cloud engine, owned by the context */
+struct Icp3dState {
+  void* d_arena = nullptr; size_t d_bytes = 0;
+  void* h_arena = nullptr; size_t h_bytes = 0;
+};
+
+void icp3d_free(void* p) {
+  Icp3dState* s = static_cast<Icp3dState*>(p);
+  cudaFree(s->d_arena);
+  cudaFreeHost(s->h_arena);
+  delete s;
+}
+
+inline size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+}  // namespace
+
+extern "C" int32_t rst_icp3d_pairs(rst_ctx* c, const rst_cloud* src, const rst_cloud* dst, int32_t n_pairs, int32_t max_iter,
+                                   float grid_cell, float* poses_inout, rst_icp3d_result* results, int32_t* nbrs_out,
+                                   float* weights_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  auto fail = [&](int code, const std::string& m) { rst::ctx_set_error(c, m); return code; };
+  if (!src || !dst || !poses_inout || n_pairs < 0 || max_iter < 0) return fail(RST_ERR_INVALID_ARG, "null clouds/poses or negative count");
+  if (n_pairs == 0) return RST_OK;
+#define ICP_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess) return fail(RST_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+  ICP_CUDA(cudaSetDevice(rst::ctx_device(c)));
+  cudaStream_t stream = rst::ctx_stream(c);
+  void (**free_fn)(void*) = nullptr;
+  void** slot = rst::ctx_ext_slot(c, &free_fn);
+  if (!*slot) { *slot = new Icp3dState(); *free_fn = icp3d_free; }
+  Icp3dState* st = static_cast<Icp3dState*>(*slot);
+
+  // arena layout (same offsets on host staging and device for the uploaded part)
+  size_t off = 0;
+  const size_t o_desc = off; off = align_up(off + sizeof(PairDesc) * n_pairs);
+  const size_t o_pose = off; off = align_up(off + sizeof(float) * 16 * n_pairs);
+  std::vector<size_t> o_src(n_pairs), o_dst(n_pairs);
+  size_t n_src_total = 0;
+  for (int i = 0; i < n_pairs; ++i) {
+    if (src[i].n < 0 || dst[i].n < 0 || (src[i].n > 0 && !src[i].xyz) || (dst[i].n > 0 && !dst[i].xyz))
+      return fail(RST_ERR_INVALID_ARG, "bad cloud");
+    o_src[i] = off; off = align_up(off + sizeof(float) * 3 * (size_t)src[i].n);
+    o_dst[i] = off; off = align_up(off + sizeof(float) * 3 * (size_t)dst[i].n);
+    n_src_total += (size_t)src[i].n;
+  }
+  const size_t upload_bytes = off;
+  const size_t o_res = off; off = align_up(off + sizeof(rst_icp3d_result) * n_pairs);
+  std::vector<size_t> o_nbr(n_pairs), o_w(n_pairs);
+  const size_t o_nbr0 = off;
+  for (int i = 0; i < n_pairs; ++i) { o_nbr[i] = off; off += sizeof(int) * (size_t)src[i].n; }
+  off = align_up(off);
+  const size_t o_w0 = off;
+  for (int i = 0; i < n_pairs; ++i) { o_w[i] = off; off += sizeof(float) * (size_t)src[i].n; }
+  off = align_up(off);
+  const size_t download_end = off;
+  std::vector<size_t> o_cs(n_pairs), o_cf(n_pairs), o_sorted(n_pairs);
+  for (int i = 0; i < n_pairs; ++i) {
+    o_cs[i] = off; off = align_up(off + sizeof(int) * (kCellCap + 1));
+    o_cf[i] = off; off = align_up(off + sizeof(int) * kCellCap);
+    o_sorted[i] = off; off = align_up(off + sizeof(float4) * (size_t)dst[i].n);
+  }
+  const size_t total = off;
+  if (st->d_bytes < total) {
+    ICP_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(st->d_arena); st->d_arena = nullptr; st->d_bytes = 0;
+    ICP_CUDA(cudaMalloc(&st->d_arena, total));
+    st->d_bytes = total;
+  }
+  if (st->h_bytes < download_end) {
+    ICP_CUDA(cudaStreamSynchronize(stream));
+    cudaFreeHost(st->h_arena); st->h_arena = nullptr; st->h_bytes = 0;
+    ICP_CUDA(cudaMallocHost(&st->h_arena, download_end));
+    st->h_bytes = download_end;
+  }
+  char* H = static_cast<char*>(st->h_arena);
+  char* D = static_cast<char*>(st->d_arena);
+  PairDesc* hd = reinterpret_cast<PairDesc*>(H + o_desc);
+  for (int i = 0; i < n_pairs; ++i) {
+    std::memcpy(H + o_src[i], src[i].xyz, sizeof(float) * 3 * (size_t)src[i].n);
+    std::memcpy(H + o_dst[i], dst[i].xyz, sizeof(float) * 3 * (size_t)dst[i].n);
+    PairDesc d;
+    d.src = reinterpret_cast<const float*>(D + o_src[i]); d.dst = reinterpret_cast<const float*>(D + o_dst[i]);
+    d.n = src[i].n; d.m = dst[i].n;
+    d.cell_start = reinterpret_cast<int*>(D + o_cs[i]); d.cell_fill = reinterpret_cast<int*>(D + o_cf[i]);
+    d.sorted = reinterpret_cast<float4*>(D + o_sorted[i]);
+    d.nbr = reinterpret_cast<int*>(D + o_nbr[i]); d.w = reinterpret_cast<float*>(D + o_w[i]);
+    d.pose = reinterpret_cast<float*>(D + o_pose) + 16 * i;
+    d.res = reinterpret_cast<rst_icp3d_result*>(D + o_res) + i;
+    hd[i] = d;
+  }
+  std::memcpy(H + o_pose, poses_inout, sizeof(float) * 16 * n_pairs);
+  ICP_CUDA(cudaMemcpyAsync(D, H, upload_bytes, cudaMemcpyHostToDevice, stream));
+  ICP_CUDA(cudaMemsetAsync(D + o_res, 0, sizeof(rst_icp3d_result) * n_pairs, stream));
+  k_icp3d<<<n_pairs, kThreads, 0, stream>>>(reinterpret_cast<const PairDesc*>(D + o_desc), max_iter, grid_cell);
+  ICP_CUDA(cudaGetLastError());
+  rst::ctx_count_launches(c, 1);
+  ICP_CUDA(cudaMemcpyAsync(H + o_pose, D + o_pose, sizeof(float) * 16 * n_pairs, cudaMemcpyDeviceToHost, stream));
+  const bool want_corr = nbrs_out || weights_out;
+  ICP_CUDA(cudaMemcpyAsync(H + o_res, D + o_res, (want_corr ? download_end : o_nbr0) - o_res, cudaMemcpyDeviceToHost, stream));
+  ICP_CUDA(cudaStreamSynchronize(stream));
+  std::memcpy(poses_inout, H + o_pose, sizeof(float) * 16 * n_pairs);
+  if (results) std::memcpy(results, H + o_res, sizeof(rst_icp3d_result) * n_pairs);
+  if (nbrs_out) std::memcpy(nbrs_out, H + o_nbr0, sizeof(int) * n_src_total);
+  if (weights_out) std::memcpy(weights_out, H + o_w0, sizeof(float) * n_src_total);
+#undef ICP_CUDA
+  return RST_OK;
+}

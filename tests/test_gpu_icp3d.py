@@ -1,0 +1,88 @@
+"""GPU: the cloud-based engine (rst_icp3d_pairs) against Oracle-R, the restatement of the reference's
+AlignIcp3d (align_icp.cpp:73-167). NN indices and weights bit-exact for one iteration from the same
+pose, cross-covariance within 1e-4 relative, final poses within 1e-4 m / 1e-4 rad."""
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import oracle as O
+from realsensetracker_b200 import Aligner, AlignIcp3d, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(ROOT / "tests" / "golden" / "oracle_r.npz")
+GN = np.load(ROOT / "tests" / "golden" / "oracle_n_160x120.npz")
+
+
+@pytest.fixture(scope="module")
+def al():
+    a = Aligner(16, 16, 2, 1)
+    yield a
+    a.close()
+
+
+def depth_clouds(i_src, i_dst, voxel=0.05):
+    intr = tuple(GN["intr"])
+    s = O.downsample_voxel(O.remove_nans(O.backproject(GN["frames"][i_src], intr)), voxel)
+    d = O.downsample_voxel(O.remove_nans(O.backproject(GN["frames"][i_dst], intr)), voxel)
+    return s, d
+
+
+@pytest.mark.parametrize("case", ["random", "depth"])
+def test_single_iteration_is_bit_exact(al, case):
+    if case == "random":
+        src, dst, T0 = GOLD["src"], GOLD["dst"], np.eye(4)
+    else:
+        src, dst = depth_clouds(1, 0)
+        T0 = synth.make_pose(synth.rotvec_to_R([0.01, -0.02, 0.01]), [0.02, 0.01, -0.03])
+    ok_o, T_o, ex_o = O.align_icp3d(src, dst, 1, T0=T0, details=True)
+    ok_g, T_g, ex_g = al.icp3d_pairs([src], [dst], 1, T0=T0, details=True)
+    assert ok_g[0] == ok_o
+    assert np.array_equal(ex_g[0]["nbrs"], ex_o["nbrs"]), f"{(ex_g[0]['nbrs'] != ex_o['nbrs']).sum()} NN indices differ"
+    assert np.array_equal(ex_g[0]["weights"], ex_o["weights"])
+    assert np.allclose(ex_g[0]["cov"], ex_o["cov"], rtol=1e-4, atol=1e-4 * np.abs(ex_o["cov"]).max())
+    assert abs(ex_g[0]["mean_cost"] - ex_o["mean_cost"]) <= 1e-5 * max(ex_o["mean_cost"], 1e-6)
+    dt, dr = synth.pose_error(T_g[0], T_o)
+    assert dt < 1e-5 and dr < 1e-5
+
+
+def test_full_run_matches_oracle_r_and_known_motion(al):
+    src, dst = GOLD["src"], GOLD["dst"]
+    ok_o, T_o, ex_o = O.align_icp3d(src, dst, 128, details=True)
+    ok_g, T_g, ex_g = al.icp3d_pairs([src], [dst], 128, details=True)
+    dt, dr = synth.pose_error(T_g[0], T_o)
+    assert ok_g[0] and dt < 1e-4 and dr < 1e-4, (dt, dr)
+    assert synth.pose_error(T_g[0], GOLD["T_small"]) < (1e-4, 1e-4)       # rs_align_app.cpp:257-263 self-test
+    assert (ex_g[0]["nbrs"] == ex_o["nbrs"]).mean() > 0.999
+    assert abs(ex_g[0]["mu"] - 1.0 / 1.4 ** 15) < 1e-6
+    ok1, T1 = AlignIcp3d(src, dst, 128)                                     # the reference's signature
+    assert ok1 and np.array_equal(T1, T_g[0])
+
+
+def test_batch_of_depth_clouds_and_determinism(al):
+    pairs = [depth_clouds(1, 0), depth_clouds(2, 1), depth_clouds(2, 0)]
+    S, D = [p[0] for p in pairs], [p[1] for p in pairs]
+    ok, T = al.icp3d_pairs(S, D, 128)
+    ok2, T2 = al.icp3d_pairs(S, D, 128)
+    assert ok.all() and np.array_equal(T, T2)
+    for i in range(3):
+        ok_o, T_o = O.align_icp3d(S[i], D[i], 128)
+        dt, dr = synth.pose_error(T[i], T_o)
+        assert dt < 1e-4 and dr < 1e-4, (i, dt, dr)
+    one_ok, one_T = al.icp3d_pairs(S[1:2], D[1:2], 128)
+    assert np.array_equal(one_T[0], T[1])                                   # independent of the batch
+
+
+def test_failure_and_edge_cases(al):
+    src, dst = GOLD["src"], GOLD["dst"]
+    ok, T = al.icp3d_pairs([src[:2]], [dst], 5)
+    assert not ok[0] and np.array_equal(T[0], np.eye(4))                    # < 3 points -> false, pose untouched
+    ok, T = al.icp3d_pairs([src], [dst], 0, T0=GOLD["T_small"])
+    assert np.allclose(T[0], GOLD["T_small"], atol=1e-7)                    # 0 iterations: pose passes through
+    far = src + np.float32(50.0)                                            # every query far outside the dst grid
+    ok_o, T_o, ex_o = O.align_icp3d(far, dst, 1, details=True)
+    ok_g, T_g, ex_g = al.icp3d_pairs([far], [dst], 1, details=True)
+    assert np.array_equal(ex_g[0]["nbrs"], ex_o["nbrs"])
+    dup = np.concatenate([dst, dst[:50]])                                   # exact ties -> lowest index, like the oracle
+    ok_o, T_o, ex_o = O.align_icp3d(src, dup, 1, details=True)
+    ok_g, T_g, ex_g = al.icp3d_pairs([src], [dup], 1, details=True)
+    assert np.array_equal(ex_g[0]["nbrs"], ex_o["nbrs"])
