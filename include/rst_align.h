@@ -284,6 +284,22 @@ int32_t rst_icp3d_pairs(rst_ctx* ctx, const rst_cloud* src, const rst_cloud* dst
                         int32_t max_iter, float grid_cell, float* poses_inout,
                         rst_icp3d_result* results, int32_t* nbrs_out, float* weights_out);
 
+/* The reference caller's whole per-pair sequence on the device, from depth frames
+ * (rs_replay_app.cpp:229,246-251): back-projection with invalid pixels at the origin
+ * (rs_driver.cpp:83-88,201-202) -> RemoveNans -> DownsampleVoxel(voxel) (first point per voxel, in
+ * first-occurrence order; voxel <= 0 skips the decimation) -> AlignIcp3d(max_iter).
+ * `frames`: the n_frames unique HOST frames; pair i aligns frames[src_idx[i]] onto
+ * frames[dst_idx[i]] (a sequence is src_idx = 1..n-1, dst_idx = 0..n-2, every frame converted once).
+ * counts_out (nullable, n_frames): points in every frame's cloud. */
+int32_t rst_icp3d_depth(rst_ctx* ctx, const rst_frame* frames, int32_t n_frames, const int32_t* src_idx,
+                        const int32_t* dst_idx, int32_t n_pairs, const rst_intrinsics* intr,
+                        float depth_scale, float voxel, int32_t max_iter, float grid_cell,
+                        float* poses_inout, rst_icp3d_result* results, int32_t* counts_out);
+
+/* Reads back (host xyz_out, n_points x 3) the cloud of one frame of the last rst_icp3d_depth call. */
+int32_t rst_icp3d_read_cloud(rst_ctx* ctx, int32_t frame_index, int32_t width, int32_t height,
+                             int32_t n_frames, float* xyz_out, int32_t n_points);
+
 /* Number of kernel launches this context has issued so far (bench evidence). */
 int64_t rst_launch_count(const rst_ctx* ctx);
 

@@ -157,6 +157,30 @@ class Aligner:
             o += m
         return ok, T, out
 
+    def icp3d_depth(self, frames: np.ndarray, src_idx, dst_idx, intr, depth_scale: float = 0.001, voxel: float = 0.05,
+                    max_iter: int = 128, T0=None, grid_cell: float = 0.1):
+        """The reference caller's per-pair sequence from depth frames (rs_replay_app.cpp:229,246-251), on the GPU.
+        frames [n,h,w] uint16; returns (ok, poses, mean_cost [n_pairs], cloud sizes [n_frames])."""
+        s = np.ascontiguousarray(src_idx, dtype=np.int32)
+        d = np.ascontiguousarray(dst_idx, dtype=np.int32)
+        n = len(s)
+        K = Intrinsics(*intr)
+        poses = pose_to_cm(np.broadcast_to(np.eye(4) if T0 is None else T0, (n, 4, 4))).copy()
+        res = (N.Icp3dResult * max(n, 1))()
+        counts = np.zeros(frames.shape[0], dtype=np.int32)
+        self._icp3d_shape = (frames.shape[2], frames.shape[1], frames.shape[0])
+        self._check(self._lib.rst_icp3d_depth(self._ctx, _frames(frames), frames.shape[0], s.ctypes.data, d.ctypes.data, n,
+                                              C.byref(K), depth_scale, voxel, max_iter, grid_cell, poses.ctypes.data,
+                                              C.addressof(res), counts.ctypes.data))
+        return (np.array([res[i].ok != 0 for i in range(n)]), cm_to_pose(poses),
+                np.array([res[i].mean_cost for i in range(n)]), counts)
+
+    def icp3d_read_cloud(self, frame_index: int, n_points: int) -> np.ndarray:
+        w, h, nf = self._icp3d_shape
+        out = np.empty((n_points, 3), dtype=np.float32)
+        self._check(self._lib.rst_icp3d_read_cloud(self._ctx, frame_index, w, h, nf, out.ctypes.data, n_points))
+        return out
+
     # ---- staged API ---------------------------------------------------------------------------
     def begin(self, w: int, h: int, intr, params: Params):
         K = Intrinsics(*intr)

@@ -33,7 +33,9 @@ constexpr int kCellCap = 1 << 18;  // grid cells per pair (1 MiB of cell_start)
 struct PairDesc {
   const float* src;   // n x 3
   const float* dst;   // m x 3
-  int n, m;
+  int n, m;           // point counts, or ...
+  const int* n_ptr;   // ... read from device memory when the clouds were produced on the device
+  const int* m_ptr;
   int* cell_start;    // [kCellCap + 1]
   int* cell_fill;     // [kCellCap]
   float4* sorted;     // m: x, y, z, original index (bit pattern)
@@ -209,7 +211,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
   __shared__ int s_scan[kWarps];
   __shared__ Grid s_grid;
 
-  const PairDesc P = descs[blockIdx.x];
+  PairDesc P = descs[blockIdx.x];
+  if (P.n_ptr) P.n = *P.n_ptr;
+  if (P.m_ptr) P.m = *P.m_ptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (P.n < 3 || P.m < 3) {  // align_icp.cpp:77-79: false, pose untouched
     if (tid == 0 && P.res) { rst_icp3d_result r{}; *P.res = r; }
@@ -371,6 +375,103 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// depth frame -> the cloud the reference's caller aligns (rs_replay_app.cpp:229,246-247):
+// back-projection with invalid pixels mapped to the origin (rs_driver.cpp:83-88,201-202), RemoveNans
+// (point_cloud_utils.cpp:163-174; nothing to drop: the back-projection emits no NaN) and
+// DownsampleVoxel (point_cloud_utils.cpp:34-68): key = floor(p / voxel), the FIRST point of a voxel
+// wins. The reference's output order is unordered_map iteration order (implementation-defined);
+// here it is first-occurrence order, which is deterministic. One 1024-thread block per frame:
+// pass 1 inserts atomicMin(pixel index) per voxel into an open-addressing hash table, pass 2 keeps
+// the winners with an order-preserving block scan.
+// ----------------------------------------------------------------------------------------------
+struct CloudifyDesc {
+  const uint16_t* depth;           // dense w*h
+  unsigned long long* keys;        // [cap], 0 = empty
+  int* vals;                       // [cap]
+  float* cloud;                    // out, up to w*h points
+  int* count;                      // out
+};
+
+constexpr unsigned long long kEmptyKey = 0ull;
+
+__device__ __forceinline__ void backproject_px(const uint16_t* depth, int i, int w, float fx, float fy, float cx, float cy,
+                                               float scale, float* p) {
+  const uint32_t d = depth[i];
+  if (d == 0u) { p[0] = p[1] = p[2] = 0.f; return; }  // invalid -> origin, kept (rs_driver.cpp:83-88)
+  const int v = i / w, u = i - v * w;
+  const float z = mulrn((float)d, scale);
+  p[0] = __fdiv_rn(mulrn(subrn((float)u, cx), z), fx);
+  p[1] = __fdiv_rn(mulrn(subrn((float)v, cy), z), fy);
+  p[2] = z;
+}
+
+__device__ __forceinline__ unsigned long long voxel_key(const float* p, float voxel) {
+  // floor(p / voxel) per axis (point_cloud_utils.cpp:41-42), 21 bits each, +1 so that 0 stays "empty"
+  const long long kx = (long long)floorf(__fdiv_rn(p[0], voxel)) + (1 << 20);
+  const long long ky = (long long)floorf(__fdiv_rn(p[1], voxel)) + (1 << 20);
+  const long long kz = (long long)floorf(__fdiv_rn(p[2], voxel)) + (1 << 20);
+  return (((unsigned long long)(kx & 0x1FFFFF) << 42) | ((unsigned long long)(ky & 0x1FFFFF) << 21) | (unsigned long long)(kz & 0x1FFFFF)) + 1ull;
+}
+
+__device__ __forceinline__ uint32_t hash_key(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return (uint32_t)k;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_cloudify(const CloudifyDesc* __restrict__ descs, int w, int h, float fx, float fy,
+                                                          float cx, float cy, float scale, float voxel, uint32_t cap_mask) {
+  __shared__ int s_scan[kWarps];
+  __shared__ int s_base;
+  const CloudifyDesc D = descs[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = w * h;
+  const bool decimate = voxel > 0.f;
+  if (decimate) {
+    for (int i = tid; i < n; i += kThreads) {
+      float p[3];
+      backproject_px(D.depth, i, w, fx, fy, cx, cy, scale, p);
+      const unsigned long long key = voxel_key(p, voxel);
+      uint32_t slot = hash_key(key) & cap_mask;
+      for (;;) {
+        const unsigned long long prev = atomicCAS(D.keys + slot, kEmptyKey, key);
+        if (prev == kEmptyKey || prev == key) { atomicMin(D.vals + slot, i); break; }
+        slot = (slot + 1) & cap_mask;
+      }
+    }
+    __syncthreads();
+  }
+  // order-preserving compaction: contiguous segment per thread, exclusive scan of the winner counts
+  const int per = (n + kThreads - 1) / kThreads;
+  const int i0 = tid * per, i1 = min(i0 + per, n);
+  auto is_winner = [&](int i, float* p) -> bool {
+    backproject_px(D.depth, i, w, fx, fy, cx, cy, scale, p);
+    if (!decimate) return true;
+    const unsigned long long key = voxel_key(p, voxel);
+    uint32_t slot = hash_key(key) & cap_mask;
+    while (D.keys[slot] != key) slot = (slot + 1) & cap_mask;
+    return D.vals[slot] == i;
+  };
+  int local = 0;
+  float p[3];
+  for (int i = i0; i < i1; ++i) local += is_winner(i, p) ? 1 : 0;
+  int incl = local;
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) s_scan[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = s_scan[lane];
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+    s_scan[lane] = v;
+  }
+  __syncthreads();
+  int pos = incl - local + (warp > 0 ? s_scan[warp - 1] : 0);
+  for (int i = i0; i < i1; ++i)
+    if (is_winner(i, p)) { D.cloud[3 * pos] = p[0]; D.cloud[3 * pos + 1] = p[1]; D.cloud[3 * pos + 2] = p[2]; ++pos; }
+  if (tid == kThreads - 1) *D.count = incl - local + (warp > 0 ? s_scan[warp - 1] : 0) + local;
+  (void)s_base;
+}
+
 /* grow-only device/pinned arenas of the cloud engine, owned by the context */
 struct Icp3dState {
   void* d_arena = nullptr; size_t d_bytes = 0;
@@ -457,7 +558,7 @@ extern "C" int32_t rst_icp3d_pairs(rst_ctx* c, const rst_cloud* src, const rst_c
     std::memcpy(H + o_dst[i], dst[i].xyz, sizeof(float) * 3 * (size_t)dst[i].n);
     PairDesc d;
     d.src = reinterpret_cast<const float*>(D + o_src[i]); d.dst = reinterpret_cast<const float*>(D + o_dst[i]);
-    d.n = src[i].n; d.m = dst[i].n;
+    d.n = src[i].n; d.m = dst[i].n; d.n_ptr = nullptr; d.m_ptr = nullptr;
     d.cell_start = reinterpret_cast<int*>(D + o_cs[i]); d.cell_fill = reinterpret_cast<int*>(D + o_cf[i]);
     d.sorted = reinterpret_cast<float4*>(D + o_sorted[i]);
     d.nbr = reinterpret_cast<int*>(D + o_nbr[i]); d.w = reinterpret_cast<float*>(D + o_w[i]);
@@ -480,5 +581,147 @@ extern "C" int32_t rst_icp3d_pairs(rst_ctx* c, const rst_cloud* src, const rst_c
   if (nbrs_out) std::memcpy(nbrs_out, H + o_nbr0, sizeof(int) * n_src_total);
   if (weights_out) std::memcpy(weights_out, H + o_w0, sizeof(float) * n_src_total);
 #undef ICP_CUDA
+  return RST_OK;
+}
+
+/* Depth frames in: the reference caller's whole per-pair sequence on the device
+ * (rs_replay_app.cpp:229,246-251): back-project -> RemoveNans -> DownsampleVoxel(voxel) -> AlignIcp3d.
+ * `frames` are the unique frames (host, dense or strided); pair i aligns frames[src_idx[i]] onto
+ * frames[dst_idx[i]]. counts_out (nullable): number of points of every frame's cloud. */
+extern "C" int32_t rst_icp3d_depth(rst_ctx* c, const rst_frame* frames, int32_t n_frames, const int32_t* src_idx,
+                                   const int32_t* dst_idx, int32_t n_pairs, const rst_intrinsics* intr, float depth_scale,
+                                   float voxel, int32_t max_iter, float grid_cell, float* poses_inout,
+                                   rst_icp3d_result* results, int32_t* counts_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  auto fail = [&](int code, const std::string& m) { rst::ctx_set_error(c, m); return code; };
+  if (!frames || !src_idx || !dst_idx || !intr || !poses_inout || n_frames < 1 || n_pairs < 0 || max_iter < 0)
+    return fail(RST_ERR_INVALID_ARG, "null argument or negative count");
+  if (!(depth_scale > 0.f) || !(intr->fx > 0.f) || !(intr->fy > 0.f)) return fail(RST_ERR_INVALID_ARG, "depth_scale and focal lengths must be positive");
+  const int w = frames[0].width, h = frames[0].height;
+  if (w < 1 || h < 1 || (int64_t)w * h > (1 << 24)) return fail(RST_ERR_INVALID_ARG, "bad frame size");
+  for (int i = 0; i < n_frames; ++i)
+    if (!frames[i].depth || frames[i].width != w || frames[i].height != h || frames[i].depth_stride_bytes < 2 * w)
+      return fail(RST_ERR_INVALID_ARG, "frames differ in size / null depth / bad stride");
+  for (int i = 0; i < n_pairs; ++i)
+    if (src_idx[i] < 0 || src_idx[i] >= n_frames || dst_idx[i] < 0 || dst_idx[i] >= n_frames) return fail(RST_ERR_INVALID_ARG, "frame index out of range");
+#define ICP_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess) return fail(RST_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+  ICP_CUDA(cudaSetDevice(rst::ctx_device(c)));
+  cudaStream_t stream = rst::ctx_stream(c);
+  void (**free_fn)(void*) = nullptr;
+  void** slot = rst::ctx_ext_slot(c, &free_fn);
+  if (!*slot) { *slot = new Icp3dState(); *free_fn = icp3d_free; }
+  Icp3dState* st = static_cast<Icp3dState*>(*slot);
+
+  const size_t npx = (size_t)w * h;
+  uint32_t cap = 1;
+  while (cap < 2 * npx) cap <<= 1;  // load factor <= 0.5 even if every pixel is its own voxel
+  const bool decimate = voxel > 0.f;
+  size_t off = 0;
+  const size_t o_cdesc = off; off = align_up(off + sizeof(CloudifyDesc) * n_frames);
+  const size_t o_pdesc = off; off = align_up(off + sizeof(PairDesc) * (size_t)(n_pairs > 0 ? n_pairs : 1));
+  const size_t o_pose = off; off = align_up(off + sizeof(float) * 16 * (size_t)(n_pairs > 0 ? n_pairs : 1));
+  const size_t upload_bytes = off;
+  const size_t o_res = off; off = align_up(off + sizeof(rst_icp3d_result) * (size_t)(n_pairs > 0 ? n_pairs : 1));
+  const size_t o_cnt = off; off = align_up(off + sizeof(int) * n_frames);
+  const size_t download_end = off;
+  const size_t o_depth = off; off = align_up(off + npx * 2 * n_frames);
+  const size_t o_cloud = off; off = align_up(off + npx * 12 * n_frames);
+  const size_t o_keys = off; off = align_up(off + (decimate ? (size_t)cap * 8 * n_frames : 0));
+  const size_t o_vals = off; off = align_up(off + (decimate ? (size_t)cap * 4 * n_frames : 0));
+  std::vector<size_t> o_cs(n_pairs), o_cf(n_pairs), o_sorted(n_pairs), o_nbr(n_pairs), o_w(n_pairs);
+  for (int i = 0; i < n_pairs; ++i) {
+    o_cs[i] = off; off = align_up(off + sizeof(int) * (kCellCap + 1));
+    o_cf[i] = off; off = align_up(off + sizeof(int) * kCellCap);
+    o_sorted[i] = off; off = align_up(off + sizeof(float4) * npx);
+    o_nbr[i] = off; off = align_up(off + sizeof(int) * npx);
+    o_w[i] = off; off = align_up(off + sizeof(float) * npx);
+  }
+  const size_t total = off;
+  if (st->d_bytes < total) {
+    ICP_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(st->d_arena); st->d_arena = nullptr; st->d_bytes = 0;
+    ICP_CUDA(cudaMalloc(&st->d_arena, total));
+    st->d_bytes = total;
+  }
+  if (st->h_bytes < download_end) {
+    ICP_CUDA(cudaStreamSynchronize(stream));
+    cudaFreeHost(st->h_arena); st->h_arena = nullptr; st->h_bytes = 0;
+    ICP_CUDA(cudaMallocHost(&st->h_arena, download_end));
+    st->h_bytes = download_end;
+  }
+  char* H = static_cast<char*>(st->h_arena);
+  char* D = static_cast<char*>(st->d_arena);
+  CloudifyDesc* cd = reinterpret_cast<CloudifyDesc*>(H + o_cdesc);
+  for (int f = 0; f < n_frames; ++f) {
+    cd[f].depth = reinterpret_cast<const uint16_t*>(D + o_depth + npx * 2 * f);
+    cd[f].keys = reinterpret_cast<unsigned long long*>(D + o_keys + (size_t)cap * 8 * f);
+    cd[f].vals = reinterpret_cast<int*>(D + o_vals + (size_t)cap * 4 * f);
+    cd[f].cloud = reinterpret_cast<float*>(D + o_cloud + npx * 12 * f);
+    cd[f].count = reinterpret_cast<int*>(D + o_cnt) + f;
+  }
+  PairDesc* pd = reinterpret_cast<PairDesc*>(H + o_pdesc);
+  for (int i = 0; i < n_pairs; ++i) {
+    PairDesc d;
+    d.src = cd[src_idx[i]].cloud; d.dst = cd[dst_idx[i]].cloud;
+    d.n = 0; d.m = 0; d.n_ptr = cd[src_idx[i]].count; d.m_ptr = cd[dst_idx[i]].count;
+    d.cell_start = reinterpret_cast<int*>(D + o_cs[i]); d.cell_fill = reinterpret_cast<int*>(D + o_cf[i]);
+    d.sorted = reinterpret_cast<float4*>(D + o_sorted[i]);
+    d.nbr = reinterpret_cast<int*>(D + o_nbr[i]); d.w = reinterpret_cast<float*>(D + o_w[i]);
+    d.pose = reinterpret_cast<float*>(D + o_pose) + 16 * i;
+    d.res = reinterpret_cast<rst_icp3d_result*>(D + o_res) + i;
+    pd[i] = d;
+  }
+  if (n_pairs > 0) std::memcpy(H + o_pose, poses_inout, sizeof(float) * 16 * n_pairs);
+  ICP_CUDA(cudaMemcpyAsync(D, H, upload_bytes, cudaMemcpyHostToDevice, stream));
+  for (int f = 0; f < n_frames; ++f)
+    ICP_CUDA(cudaMemcpy2DAsync(D + o_depth + npx * 2 * f, (size_t)w * 2, frames[f].depth, (size_t)frames[f].depth_stride_bytes,
+                               (size_t)w * 2, (size_t)h, cudaMemcpyHostToDevice, stream));
+  if (decimate) {
+    ICP_CUDA(cudaMemsetAsync(D + o_keys, 0, (size_t)cap * 8 * n_frames, stream));
+    ICP_CUDA(cudaMemsetAsync(D + o_vals, 0x7f, (size_t)cap * 4 * n_frames, stream));  // 0x7f7f7f7f > any pixel index
+  }
+  ICP_CUDA(cudaMemsetAsync(D + o_res, 0, sizeof(rst_icp3d_result) * (size_t)(n_pairs > 0 ? n_pairs : 1), stream));
+  k_cloudify<<<n_frames, kThreads, 0, stream>>>(reinterpret_cast<const CloudifyDesc*>(D + o_cdesc), w, h, intr->fx, intr->fy, intr->cx,
+                                                intr->cy, depth_scale, voxel, cap - 1);
+  ICP_CUDA(cudaGetLastError());
+  rst::ctx_count_launches(c, 1);
+  if (n_pairs > 0) {
+    k_icp3d<<<n_pairs, kThreads, 0, stream>>>(reinterpret_cast<const PairDesc*>(D + o_pdesc), max_iter, grid_cell);
+    ICP_CUDA(cudaGetLastError());
+    rst::ctx_count_launches(c, 1);
+    ICP_CUDA(cudaMemcpyAsync(H + o_pose, D + o_pose, sizeof(float) * 16 * n_pairs, cudaMemcpyDeviceToHost, stream));
+  }
+  ICP_CUDA(cudaMemcpyAsync(H + o_res, D + o_res, download_end - o_res, cudaMemcpyDeviceToHost, stream));
+  ICP_CUDA(cudaStreamSynchronize(stream));
+  if (n_pairs > 0) std::memcpy(poses_inout, H + o_pose, sizeof(float) * 16 * n_pairs);
+  if (results && n_pairs > 0) std::memcpy(results, H + o_res, sizeof(rst_icp3d_result) * n_pairs);
+  if (counts_out) std::memcpy(counts_out, H + o_cnt, sizeof(int) * n_frames);
+#undef ICP_CUDA
+  return RST_OK;
+}
+
+/* Reads back the cloud of frame `frame_index` produced by the last rst_icp3d_depth call (parity tests). */
+extern "C" int32_t rst_icp3d_read_cloud(rst_ctx* c, int32_t frame_index, int32_t width, int32_t height, int32_t n_frames, float* xyz_out,
+                                        int32_t n_points) {
+  if (!c || !xyz_out || frame_index < 0 || frame_index >= n_frames || n_points < 0) return RST_ERR_INVALID_ARG;
+  void (**free_fn)(void*) = nullptr;
+  void** slot = rst::ctx_ext_slot(c, &free_fn);
+  if (!*slot) return RST_ERR_INVALID_ARG;
+  Icp3dState* st = static_cast<Icp3dState*>(*slot);
+  // recompute the arena layout of rst_icp3d_depth up to the clouds
+  const size_t npx = (size_t)width * height;
+  size_t off = 0;
+  off = align_up(off + sizeof(CloudifyDesc) * n_frames);
+  CloudifyDesc d;
+  if (cudaSetDevice(rst::ctx_device(c)) != cudaSuccess) return RST_ERR_CUDA;
+  if (cudaMemcpy(&d, static_cast<char*>(st->d_arena) + sizeof(CloudifyDesc) * frame_index, sizeof(d), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return RST_ERR_CUDA;
+  if ((size_t)n_points > npx) return RST_ERR_INVALID_ARG;
+  if (cudaMemcpy(xyz_out, d.cloud, sizeof(float) * 3 * (size_t)n_points, cudaMemcpyDeviceToHost) != cudaSuccess) return RST_ERR_CUDA;
+  (void)off;
   return RST_OK;
 }

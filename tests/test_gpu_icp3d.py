@@ -86,3 +86,26 @@ def test_failure_and_edge_cases(al):
     ok_o, T_o, ex_o = O.align_icp3d(src, dup, 1, details=True)
     ok_g, T_g, ex_g = al.icp3d_pairs([src], [dup], 1, details=True)
     assert np.array_equal(ex_g[0]["nbrs"], ex_o["nbrs"])
+
+
+def test_depth_to_cloud_is_bit_exact_and_depth_icp_matches_the_reference_pipeline(al):
+    """rst_icp3d_depth = the caller's sequence rs_replay_app.cpp:229,246-251 on the device."""
+    frames, intr = GN["frames"], tuple(GN["intr"])
+    src_idx, dst_idx = [1, 2], [0, 1]                      # frame-to-frame sequence
+    ok, T, mean_cost, counts = al.icp3d_depth(frames, src_idx, dst_idx, intr, voxel=0.05, max_iter=128)
+    for f in range(3):
+        want = O.downsample_voxel(O.remove_nans(O.backproject(frames[f], intr)), 0.05)
+        assert counts[f] == len(want)
+        got = al.icp3d_read_cloud(f, int(counts[f]))
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"cloud of frame {f} differs"
+    for i in range(2):
+        ok_o, T_o, ex = O.align_depth_pair(frames[src_idx[i]], frames[dst_idx[i]], intr)
+        dt, dr = synth.pose_error(T[i], T_o)
+        assert ok[i] == ok_o and dt < 1e-4 and dr < 1e-4, (i, dt, dr)
+        assert abs(mean_cost[i] - ex["mean_cost"]) < 1e-5
+    # no decimation: the full-resolution cloud, invalid pixels at the origin (rs_driver.cpp:83-88)
+    z = frames[0].copy(); z[:40] = 0
+    ok, T, mc, counts = al.icp3d_depth(np.stack([z, frames[1]]), [1], [0], intr, voxel=0.0, max_iter=2)
+    assert counts.tolist() == [160 * 120, 160 * 120]
+    cloud = al.icp3d_read_cloud(0, 160 * 120)
+    assert np.array_equal(cloud, O.backproject(z, intr)) and (cloud[:40 * 160] == 0).all()
