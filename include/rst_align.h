@@ -68,6 +68,15 @@ enum {
   RST_ROBUST_GEMAN_MCCLURE = 2   /* w = (mu/(r^2+mu))^2    (align_icp.cpp:116-118) */
 };
 
+/* ---- block tiling of the fused ICP kernel (rst_params.tiling) ----
+ * Block extents depend on the image size and this switch only — never on the batch size — so
+ * results are bit-identical across batch sizes, ranks and entry points for a given tiling; the two
+ * tilings differ from each other in the last bits (different fp32 partial-sum extents). */
+enum {
+  RST_TILING_THROUGHPUT = 0,  /* up to 8192 pixels per block: fewest partials, best for batches   */
+  RST_TILING_LATENCY = 1      /* 512 pixels per block: a single pair spreads over all 148 SMs      */
+};
+
 /* Pin-hole intrinsics of the finest level; K = [[fx,0,cx],[0,fy,cy],[0,0,1]]
  * (rs_driver.cpp:264-280).  No distortion. */
 typedef struct rst_intrinsics {
@@ -104,7 +113,8 @@ typedef struct rst_params {
   int32_t min_count;              /* minimum associations per iteration         */
   float damping;                  /* added to diag(A) before the solve          */
   float photo_weight;             /* lambda of the photometric term, 0 = off    */
-  int32_t reserved[4];
+  int32_t tiling;                 /* RST_TILING_*: how pixels are cut into blocks */
+  int32_t reserved[3];
 } rst_params;
 
 /* Per-pair result statistics. A/b/sum_wr2/count belong to the LAST evaluated

@@ -14,6 +14,7 @@ RST_MAX_LEVELS = 4
 RST_OK, RST_ERR_INVALID_ARG, RST_ERR_NO_DEVICE, RST_ERR_CUDA, RST_ERR_CAPACITY, RST_ERR_ALIGNMENT, RST_ERR_ARCH = range(7)
 RST_STATUS_OK, RST_STATUS_TOO_FEW, RST_STATUS_DEGENERATE, RST_STATUS_NON_FINITE = 0, 1, 2, 4
 RST_ROBUST_NONE, RST_ROBUST_HUBER, RST_ROBUST_GEMAN_MCCLURE = 0, 1, 2
+RST_TILING_THROUGHPUT, RST_TILING_LATENCY = 0, 1
 
 ERR_NAMES = {0: "RST_OK", 1: "RST_ERR_INVALID_ARG", 2: "RST_ERR_NO_DEVICE", 3: "RST_ERR_CUDA",
              4: "RST_ERR_CAPACITY", 5: "RST_ERR_ALIGNMENT", 6: "RST_ERR_ARCH"}
@@ -40,7 +41,7 @@ class Params(C.Structure):
                 ("dist_max", C.c_float), ("normal_cos_min", C.c_float), ("normal_depth_tol", C.c_float),
                 ("pyr_depth_tol", C.c_int32), ("robust_kind", C.c_int32), ("robust_scale", C.c_float),
                 ("min_count", C.c_int32), ("damping", C.c_float), ("photo_weight", C.c_float),
-                ("reserved", C.c_int32 * 4)]
+                ("tiling", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class Stats(C.Structure):

@@ -277,6 +277,7 @@ int32_t rst_begin(rst_ctx* c, int32_t width, int32_t height, const rst_intrinsic
   if (!(P.depth_scale > 0.f) || !(P.dist_max > 0.f) || !(P.z_max > P.z_min) || !(intr->fx > 0.f) || !(intr->fy > 0.f))
     return fail(c, RST_ERR_INVALID_ARG, "depth_scale, dist_max, z range and focal lengths must be positive");
   if (P.robust_kind < 0 || P.robust_kind > 2) return fail(c, RST_ERR_INVALID_ARG, "unknown robust_kind");
+  if (P.tiling < 0 || P.tiling > 1) return fail(c, RST_ERR_INVALID_ARG, "unknown tiling");
   if (P.robust_kind != RST_ROBUST_NONE && !(P.robust_scale > 0.f)) return fail(c, RST_ERR_INVALID_ARG, "robust_scale must be positive");
   if ((width >> (P.num_levels - 1)) < 8 || (height >> (P.num_levels - 1)) < 8)
     return fail(c, RST_ERR_INVALID_ARG, "coarsest pyramid level smaller than 8x8");
@@ -295,7 +296,7 @@ int32_t rst_begin(rst_ctx* c, int32_t width, int32_t height, const rst_intrinsic
       // pixels per block ~ level size / 8, a power-of-two number of groups, at most kMaxGroups
       const int group_px = kChunksPerBlock * kChunkPx;
       int g = 1;
-      while (g * 2 <= kMaxGroups && (int64_t)g * 2 * group_px * 8 <= (int64_t)c->n_chunks[l] * kChunkPx) g *= 2;
+      while (P.tiling != RST_TILING_LATENCY && g * 2 <= kMaxGroups && (int64_t)g * 2 * group_px * 8 <= (int64_t)c->n_chunks[l] * kChunkPx) g *= 2;
       c->groups[l] = g;
     }
     const int cpb = kChunksPerBlock * c->groups[l];

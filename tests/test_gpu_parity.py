@@ -285,3 +285,21 @@ def test_async_submit_wait_equals_blocking_call(seq640):
             assert np.array_equal(Tp, Tref)
     finally:
         a.close(); b.close()
+
+
+def test_latency_tiling_matches_oracle_and_is_batch_invariant(seq640):
+    frames, gt, intr = seq640
+    P = default_params(tiling=N.RST_TILING_LATENCY)
+    Po = O.default_params()
+    al = Aligner(640, 480, 8, 4)
+    try:
+        T, st = al.align_pairs(frames[1:4], frames[0:3], intr, P)
+        T1, _ = al.align_pairs(frames[2:3], frames[1:2], intr, P)
+        assert np.array_equal(T1[0], T[1])
+        for i in range(3):
+            To, so = O.align_pair(frames[i + 1], frames[i], intr, Po)
+            _check_pose(T[i], To, gt[i])
+        with pytest.raises(Exception):
+            al.align_pairs(frames[1:2], frames[0:1], intr, default_params(tiling=7))
+    finally:
+        al.close()
