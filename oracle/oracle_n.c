@@ -105,7 +105,7 @@ void on_geometry(const uint16_t* D, const on_level* L, const rst_params* P, floa
       float ny = fmaf(az, bx, -(ax * bz));
       float nz = fmaf(ax, by, -(ay * bx));
       const float len2 = fmaf(nz, nz, fmaf(ny, ny, nx * nx));
-      if (!(len2 > 0.0f) || !(len2 < INFINITY)) continue;
+      if (!(len2 >= 1e-30f) || !(len2 < INFINITY)) continue; /* degenerate normal */
       float inv = 1.0f / sqrtf(len2);
       /* orient toward the camera: flip if n . V > 0 (point_cloud_utils.cpp:210-214) */
       const float dotv = fmaf(nz, z, fmaf(ny, ky * z, nx * (kx * z)));

@@ -396,7 +396,7 @@ static int32_t preprocess_impl(rst_ctx* c, int first_slot, int n, bool write_geo
       a.next_w = c->geom[l + 1].w; a.next_h = c->geom[l + 1].h;
     }
     a.first_slot = first_slot;
-    a.depth_scale = c->P.depth_scale; a.z_min = c->P.z_min; a.z_max = c->P.z_max;
+    a.depth_scale = c->P.depth_scale; a.d_lo = c->d_lo; a.d_span = c->d_span;
     a.normal_depth_tol = c->P.normal_depth_tol; a.pyr_tol = c->P.pyr_depth_tol;
     const int ph = prof_begin(c, 0, l);
     RST_CUDA(c, launch_preprocess(a, n, c->stream));

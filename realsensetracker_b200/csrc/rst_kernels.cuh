@@ -43,6 +43,7 @@ constexpr int kChunkPx = 64;      // pixels one warp covers per step (2 per lane
 constexpr int kChunksPerWarp = RST_ICP_CPW; // chunks per warp per group -> 2*CPW pixels in flight per thread
 constexpr int kMaxGroups = RST_ICP_GROUP_PX / ((RST_ICP_THREADS / 32) * RST_ICP_CPW * 64);  // groups per block on large levels
 constexpr int kPxPerStage = 2 * kChunksPerWarp;  // gathers per thread per pipeline stage
+constexpr float kMinNormalLen2 = 1e-30f; // |a x b|^2 below this is a degenerate normal
 constexpr float kMinProjZ = 1e-6f; // transformed points closer than this to the camera plane are rejected
 constexpr int kChunksPerBlock = (kIcpThreads / 32) * kChunksPerWarp;  // 32 -> 2048 px
 constexpr int kTileW = 64, kTileH = 32;  // preprocess tile
@@ -69,7 +70,8 @@ struct PreArgs {
   int64_t next_frame;
   int32_t next_w, next_h;
   int32_t first_slot;
-  float depth_scale, z_min, z_max, normal_depth_tol;
+  float depth_scale, normal_depth_tol;
+  uint32_t d_lo, d_span;     // valid raw depth: (d - d_lo) <= d_span  <=>  d != 0 && z_min <= d*scale <= z_max
   int32_t pyr_tol;
 };
 
