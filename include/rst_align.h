@@ -112,7 +112,8 @@ typedef struct rst_params {
   float robust_scale;             /* Huber delta (m) or Geman-McClure mu (m^2)  */
   int32_t min_count;              /* minimum associations per iteration         */
   float damping;                  /* added to diag(A) before the solve          */
-  float photo_weight;             /* lambda of the photometric term, 0 = off    */
+  float photo_weight;             /* lambda of the photometric term (needs rst_frame.rgb), 0 = off:
+                                     cost = sum r_geo^2 + lambda * sum (I_dst(pi(p')) - I_src)^2  */
   int32_t tiling;                 /* RST_TILING_*: how pixels are cut into blocks */
   int32_t reserved[3];
 } rst_params;
@@ -250,6 +251,9 @@ int32_t rst_read_depth(rst_ctx* ctx, int32_t slot, int32_t level, uint16_t* out)
 /* Reads back the geometry map of a slot/level: width*height float4
  * {nx, ny, nz, z}; z = 0 where the vertex or the normal is invalid. */
 int32_t rst_read_geometry(rst_ctx* ctx, int32_t slot, int32_t level, float* out);
+
+/* Reads back the intensity map of a slot/level (photometric term on): width*height floats in [0,1]. */
+int32_t rst_read_intensity(rst_ctx* ctx, int32_t slot, int32_t level, float* out);
 
 /* One association + normal-equation evaluation at `level` under `pose`
  * (column-major 4x4 fp32, src->dst), without updating any pose:

@@ -61,6 +61,7 @@ def lib() -> C.CDLL:
         _lib.or_downsample_voxel.restype = C.c_int32
         _lib.on_solve.restype = C.c_int32
         _lib.on_align_pair.restype = C.c_int32
+        _lib.on_align_pair_rgbd.restype = C.c_int32
     return _lib
 
 
@@ -150,6 +151,49 @@ def align_pair(src: np.ndarray, dst: np.ndarray, intr, P: Params, T0=None):
     st = Stats()
     lib().on_align_pair(s.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), C.c_int32(w), C.c_int32(h),
                         C.byref(K), C.byref(P), pose.ctypes.data_as(C.c_void_p), C.byref(st))
+    return cm_to_pose(pose), st
+
+
+def intensity(rgb: np.ndarray) -> np.ndarray:
+    h, w, _ = rgb.shape
+    c = np.ascontiguousarray(rgb, dtype=np.uint8)
+    out = np.empty((h, w), dtype=np.float32)
+    lib().on_intensity(c.ctypes.data_as(C.c_void_p), C.c_int32(w), C.c_int32(h), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def intensity_down(I: np.ndarray) -> np.ndarray:
+    h, w = I.shape
+    a = np.ascontiguousarray(I, dtype=np.float32)
+    out = np.empty((h // 2, w // 2), dtype=np.float32)
+    lib().on_intensity_down(a.ctypes.data_as(C.c_void_p), C.c_int32(w), C.c_int32(h), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def evaluate_photo(src_depth, src_G, dst_G, src_I, dst_I, L: Level, P: Params, T, want_idx=True):
+    d = np.ascontiguousarray(src_depth, dtype=np.uint16)
+    si, di = np.ascontiguousarray(src_I, dtype=np.float32), np.ascontiguousarray(dst_I, dtype=np.float32)
+    pose = pose_to_cm(T)
+    idx = np.empty((L.h, L.w), dtype=np.int32) if want_idx else None
+    st = Stats()
+    lib().on_evaluate_photo(d.ctypes.data_as(C.c_void_p),
+                            src_G.ctypes.data_as(C.c_void_p) if src_G is not None else None,
+                            dst_G.ctypes.data_as(C.c_void_p), si.ctypes.data_as(C.c_void_p), di.ctypes.data_as(C.c_void_p),
+                            C.byref(L), C.byref(P), pose.ctypes.data_as(C.c_void_p),
+                            idx.ctypes.data_as(C.c_void_p) if want_idx else None, C.byref(st))
+    return idx, st
+
+
+def align_pair_rgbd(src, dst, src_rgb, dst_rgb, intr, P: Params, T0=None):
+    h, w = src.shape
+    s, d = np.ascontiguousarray(src, dtype=np.uint16), np.ascontiguousarray(dst, dtype=np.uint16)
+    sc, dc = np.ascontiguousarray(src_rgb, dtype=np.uint8), np.ascontiguousarray(dst_rgb, dtype=np.uint8)
+    K = Intrinsics(*intr)
+    pose = pose_to_cm(np.eye(4) if T0 is None else T0)
+    st = Stats()
+    lib().on_align_pair_rgbd(s.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p),
+                             dc.ctypes.data_as(C.c_void_p), C.c_int32(w), C.c_int32(h), C.byref(K), C.byref(P),
+                             pose.ctypes.data_as(C.c_void_p), C.byref(st))
     return cm_to_pose(pose), st
 
 

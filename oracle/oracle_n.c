@@ -115,6 +115,23 @@ void on_geometry(const uint16_t* D, const on_level* L, const rst_params* P, floa
     }
 }
 
+/* f2: grey level-0 intensity from RGB (CV_8UC3, rs_driver.cpp:212): I = (0.299 R + 0.587 G + 0.114 B) / 255 */
+void on_intensity(const uint8_t* rgb, int32_t w, int32_t h, float* I) {
+  for (size_t i = 0; i < (size_t)w * h; ++i)
+    I[i] = fmaf(0.114f, (float)rgb[3 * i + 2], fmaf(0.587f, (float)rgb[3 * i + 1], 0.299f * (float)rgb[3 * i])) * (1.0f / 255.0f);
+}
+
+/* intensity pyramid: plain 2x2 mean, ((a + b) + (c + d)) * 0.25 */
+void on_intensity_down(const float* in, int32_t w, int32_t h, float* out) {
+  const int32_t w2 = w / 2, h2 = h / 2;
+  for (int v = 0; v < h2; ++v)
+    for (int u = 0; u < w2; ++u)
+      out[v * w2 + u] = ((in[(2 * v) * w + 2 * u] + in[(2 * v) * w + 2 * u + 1]) +
+                         (in[(2 * v + 1) * w + 2 * u] + in[(2 * v + 1) * w + 2 * u + 1])) * 0.25f;
+}
+
+static inline int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
 static inline float robust_w(const rst_params* P, float r) {
   if (P->robust_kind == RST_ROBUST_HUBER) {
     const float a = fabsf(r);
@@ -129,8 +146,9 @@ static inline float robust_w(const rst_params* P, float r) {
 
 /* K3+K4: association + normal equations at one level under `pose` (col-major 4x4).
  * src_G may be NULL when the normal gate is disabled. idx may be NULL. */
-void on_evaluate(const uint16_t* src_D, const float* src_G, const float* dst_G, const on_level* L,
-                 const rst_params* P, const float* pose, int32_t* idx, rst_stats* st) {
+static void on_evaluate_impl(const uint16_t* src_D, const float* src_G, const float* dst_G, const float* src_I,
+                             const float* dst_I, const on_level* L, const rst_params* P, const float* pose,
+                             int32_t* idx, rst_stats* st) {
   const int w = L->w, h = L->h;
   const float R00 = pose[0], R10 = pose[1], R20 = pose[2];
   const float R01 = pose[4], R11 = pose[5], R21 = pose[6];
@@ -196,12 +214,55 @@ void on_evaluate(const uint16_t* src_D, const float* src_G, const float* dst_G, 
       }
       swr2 += (double)(wgt * r * r);
       ++count;
+      if (src_I && dst_I && P->photo_weight > 0.0f) {
+        /* photometric row (f2): r_I = I_dst(pi(p')) - I_src(u,v), bilinear sample clamped at the borders
+         * (sample.hpp:32-47), residual sign of photometric_cost.hpp:63; J_I = [p' x d ; d] with
+         * d = (dI/du fx/z, dI/dv fy/z, -(d_x x + d_y y)/z), scaled by sqrt(lambda). */
+        const float x0f = floorf(uf), y0f = floorf(vf);
+        const float axf = uf - x0f, ayf = vf - y0f;
+        const int x0 = clampi((int)x0f, 0, w - 1), x1 = clampi((int)x0f + 1, 0, w - 1);
+        const int y0 = clampi((int)y0f, 0, h - 1), y1 = clampi((int)y0f + 1, 0, h - 1);
+        const float I00 = dst_I[(size_t)y0 * w + x0], I10 = dst_I[(size_t)y0 * w + x1];
+        const float I01 = dst_I[(size_t)y1 * w + x0], I11 = dst_I[(size_t)y1 * w + x1];
+        const float dt = I10 - I00, db = I11 - I01;
+        const float top = fmaf(axf, dt, I00), bot = fmaf(axf, db, I01);
+        const float gv = bot - top;
+        const float val = fmaf(ayf, gv, top);
+        const float gu = fmaf(ayf, db - dt, dt);
+        const float sl = sqrtf(P->photo_weight);
+        const float rI = sl * (val - src_I[i]);
+        const float da = sl * ((gu * L->fx) * iz), dbb = sl * ((gv * L->fy) * iz);
+        const float dc = -(fmaf(da, qx_, dbb * qy_) * iz);
+        float JI[6];
+        JI[0] = fmaf(qy_, dc, -(qz_ * dbb));
+        JI[1] = fmaf(qz_, da, -(qx_ * dc));
+        JI[2] = fmaf(qx_, dbb, -(qy_ * da));
+        JI[3] = da; JI[4] = dbb; JI[5] = dc;
+        k = 0;
+        for (int a = 0; a < 6; ++a) {
+          for (int c = a; c < 6; ++c) A[k++] += (double)(JI[a] * JI[c]);
+          b[a] += (double)(JI[a] * rI);
+        }
+        swr2 += (double)(rI * rI);
+      }
     }
   memcpy(st->A, A, sizeof(A));
   memcpy(st->b, b, sizeof(b));
   st->sum_wr2 = swr2;
   st->count = (int32_t)count;
   st->rmse = count > 0 ? (float)sqrt(swr2 / (double)count) : 0.0f;
+}
+
+void on_evaluate(const uint16_t* src_D, const float* src_G, const float* dst_G, const on_level* L,
+                 const rst_params* P, const float* pose, int32_t* idx, rst_stats* st) {
+  on_evaluate_impl(src_D, src_G, dst_G, NULL, NULL, L, P, pose, idx, st);
+}
+
+/* K3+K4 with the photometric term: src_I / dst_I are the dense intensity maps of this level */
+void on_evaluate_photo(const uint16_t* src_D, const float* src_G, const float* dst_G, const float* src_I,
+                       const float* dst_I, const on_level* L, const rst_params* P, const float* pose,
+                       int32_t* idx, rst_stats* st) {
+  on_evaluate_impl(src_D, src_G, dst_G, src_I, dst_I, L, P, pose, idx, st);
 }
 
 /* K5: solve (A + damping*I) xi = -b by Cholesky in fp64. Returns a status bit. */
@@ -297,9 +358,11 @@ static void rt_to_pose(const double* Rt, float* pose) {
 /* Full coarse-to-fine alignment of one pair; dense w*h uint16 frames.
  * pose: column-major 4x4 fp32, initial guess in, result out (align_icp.cpp:82,156).
  * Returns the status word (0 = OK). */
-int32_t on_align_pair(const uint16_t* src, const uint16_t* dst, int32_t w, int32_t h,
-                      const rst_intrinsics* K, const rst_params* P, float* pose, rst_stats* st) {
+static int32_t on_align_pair_impl(const uint16_t* src, const uint16_t* dst, const uint8_t* src_rgb, const uint8_t* dst_rgb,
+                                  int32_t w, int32_t h, const rst_intrinsics* K, const rst_params* P, float* pose, rst_stats* st) {
   const int nl = P->num_levels;
+  const int photo = src_rgb && dst_rgb && P->photo_weight > 0.0f;
+  float* sI[RST_MAX_LEVELS] = {0}; float* dI[RST_MAX_LEVELS] = {0};
   uint16_t* sD[RST_MAX_LEVELS]; uint16_t* dD[RST_MAX_LEVELS];
   float* sG[RST_MAX_LEVELS]; float* dG[RST_MAX_LEVELS];
   on_level L[RST_MAX_LEVELS];
@@ -317,6 +380,11 @@ int32_t on_align_pair(const uint16_t* src, const uint16_t* dst, int32_t w, int32
     on_geometry(dD[l], &L[l], P, dG[l]);
     sG[l] = NULL;
     if (use_ngate) { sG[l] = (float*)malloc(n * 16); on_geometry(sD[l], &L[l], P, sG[l]); }
+    if (photo) {
+      sI[l] = (float*)malloc(n * 4); dI[l] = (float*)malloc(n * 4);
+      if (l == 0) { on_intensity(src_rgb, w, h, sI[0]); on_intensity(dst_rgb, w, h, dI[0]); }
+      else { on_intensity_down(sI[l - 1], L[l - 1].w, L[l - 1].h, sI[l]); on_intensity_down(dI[l - 1], L[l - 1].w, L[l - 1].h, dI[l]); }
+    }
   }
   double Rt[12];
   for (int i = 0; i < 3; ++i) {
@@ -330,7 +398,7 @@ int32_t on_align_pair(const uint16_t* src, const uint16_t* dst, int32_t w, int32
   for (int l = nl - 1; l >= 0; --l)
     for (int it = 0; it < P->iters[l]; ++it) {
       rt_to_pose(Rt, cur);
-      on_evaluate(sD[l], sG[l], dG[l], &L[l], P, cur, NULL, &s);
+      on_evaluate_impl(sD[l], sG[l], dG[l], sI[l], dI[l], &L[l], P, cur, NULL, &s);
       double xi[6];
       const int32_t rc = on_solve(s.A, s.b, s.count, P, xi);
       if (rc == RST_STATUS_OK) on_pose_update(xi, Rt); else status |= rc;
@@ -340,6 +408,17 @@ int32_t on_align_pair(const uint16_t* src, const uint16_t* dst, int32_t w, int32
   for (int i = 0; i < 16; ++i) if (!isfinite(pose[i])) status |= RST_STATUS_NON_FINITE;
   s.status = status; s.iterations = iters;
   if (st) *st = s;
-  for (int l = 0; l < nl; ++l) { free(sD[l]); free(dD[l]); free(dG[l]); free(sG[l]); }
+  for (int l = 0; l < nl; ++l) { free(sD[l]); free(dD[l]); free(dG[l]); free(sG[l]); free(sI[l]); free(dI[l]); }
   return status;
+}
+
+int32_t on_align_pair(const uint16_t* src, const uint16_t* dst, int32_t w, int32_t h,
+                      const rst_intrinsics* K, const rst_params* P, float* pose, rst_stats* st) {
+  return on_align_pair_impl(src, dst, NULL, NULL, w, h, K, P, pose, st);
+}
+
+/* RGB-D alignment: geometric + lambda * photometric (BASELINE config 4). rgb: dense w*h*3 uint8. */
+int32_t on_align_pair_rgbd(const uint16_t* src, const uint16_t* dst, const uint8_t* src_rgb, const uint8_t* dst_rgb,
+                           int32_t w, int32_t h, const rst_intrinsics* K, const rst_params* P, float* pose, rst_stats* st) {
+  return on_align_pair_impl(src, dst, src_rgb, dst_rgb, w, h, K, P, pose, st);
 }

@@ -69,7 +69,7 @@ ALIGN_SYMBOLS = [
     "rst_ctx_create", "rst_ctx_destroy", "rst_last_error", "rst_last_create_error", "rst_abi_version",
     "rst_params_default", "rst_align_pairs", "rst_align_sequence", "rst_begin", "rst_upload_frames",
     "rst_set_frames_device", "rst_preprocess", "rst_align_slots", "rst_device_results", "rst_sync",
-    "rst_level_info", "rst_read_depth", "rst_read_geometry", "rst_evaluate", "rst_launch_count",
+    "rst_level_info", "rst_read_depth", "rst_read_geometry", "rst_read_intensity", "rst_evaluate", "rst_launch_count",
     "rst_copy_results_device", "rst_profile_enable", "rst_profile_read", "rst_set_pipeline_chunk", "rst_align_pairs_async", "rst_align_sequence_async", "rst_wait", "rst_icp3d_pairs", "rst_icp3d_depth", "rst_icp3d_read_cloud",
 ]
 
@@ -145,6 +145,8 @@ def align_lib() -> C.CDLL:
         lib.rst_read_depth.restype = C.c_int32
         lib.rst_read_geometry.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         lib.rst_read_geometry.restype = C.c_int32
+        lib.rst_read_intensity.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        lib.rst_read_intensity.restype = C.c_int32
         lib.rst_evaluate.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, P(Stats)]
         lib.rst_evaluate.restype = C.c_int32
         lib.rst_launch_count.argtypes = [C.c_void_p]

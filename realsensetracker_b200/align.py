@@ -40,18 +40,20 @@ def cm_to_pose(p) -> np.ndarray:
     return np.swapaxes(p.reshape(p.shape[:-1] + (4, 4)), -1, -2).astype(np.float64)
 
 
-def _frames(arr: np.ndarray):
-    """numpy [n,h,w] uint16 (any row stride) -> (ctypes Frame array, keepalive)."""
+def _frames(arr: np.ndarray, rgb: np.ndarray | None = None):
+    """numpy depth [n,h,w] uint16 (any row stride) and optional rgb [n,h,w,3] uint8 -> ctypes Frame array."""
     assert arr.dtype == np.uint16 and arr.ndim == 3 and arr.strides[2] == 2
     n, h, w = arr.shape
+    if rgb is not None:
+        assert rgb.dtype == np.uint8 and rgb.shape == (n, h, w, 3) and rgb.strides[3] == 1 and rgb.strides[2] == 3
     fr = (Frame * n)()
     base = arr.ctypes.data
     for i in range(n):
         fr[i].depth = base + i * arr.strides[0]
-        fr[i].rgb = None
+        fr[i].rgb = rgb.ctypes.data + i * rgb.strides[0] if rgb is not None else None
         fr[i].width, fr[i].height = w, h
         fr[i].depth_stride_bytes = arr.strides[1]
-        fr[i].rgb_stride_bytes = 0
+        fr[i].rgb_stride_bytes = rgb.strides[1] if rgb is not None else 0
     return fr
 
 
@@ -87,14 +89,16 @@ class Aligner:
             raise RstError(rc, self._lib.rst_last_error(self._ctx).decode())
 
     # ---- one-call API (host frames in, poses out) -------------------------------------------
-    def align_pairs(self, src: np.ndarray, dst: np.ndarray, intr, params: Params | None = None, T0=None):
-        """src, dst: [n,h,w] uint16. Returns (poses [n,4,4], list of Stats)."""
+    def align_pairs(self, src: np.ndarray, dst: np.ndarray, intr, params: Params | None = None, T0=None,
+                    src_rgb: np.ndarray | None = None, dst_rgb: np.ndarray | None = None):
+        """src, dst: [n,h,w] uint16 (+ optional rgb [n,h,w,3] uint8 for the photometric term).
+        Returns (poses [n,4,4], list of Stats)."""
         n = src.shape[0]
         P = params if params is not None else default_params()
         K = Intrinsics(*intr)
         poses = pose_to_cm(np.broadcast_to(np.eye(4) if T0 is None else T0, (n, 4, 4))).copy()
         stats = (Stats * n)()
-        self._check(self._lib.rst_align_pairs(self._ctx, _frames(src), _frames(dst), n, C.byref(K), C.byref(P),
+        self._check(self._lib.rst_align_pairs(self._ctx, _frames(src, src_rgb), _frames(dst, dst_rgb), n, C.byref(K), C.byref(P),
                                               poses.ctypes.data, C.addressof(stats)))
         return cm_to_pose(poses), list(stats)
 
@@ -186,8 +190,8 @@ class Aligner:
         K = Intrinsics(*intr)
         self._check(self._lib.rst_begin(self._ctx, w, h, C.byref(K), C.byref(params)))
 
-    def upload(self, frames: np.ndarray, first_slot: int = 0):
-        self._check(self._lib.rst_upload_frames(self._ctx, _frames(frames), frames.shape[0], first_slot))
+    def upload(self, frames: np.ndarray, first_slot: int = 0, rgb: np.ndarray | None = None):
+        self._check(self._lib.rst_upload_frames(self._ctx, _frames(frames, rgb), frames.shape[0], first_slot))
 
     def set_frames_device(self, dev_ptr: int, n: int, row_stride_px: int, frame_stride_px: int, first_slot: int = 0):
         self._check(self._lib.rst_set_frames_device(self._ctx, dev_ptr, n, row_stride_px, frame_stride_px, first_slot))
@@ -233,6 +237,12 @@ class Aligner:
         w, h, _, _ = self.level_info(level)
         out = np.empty((h, w, 4), dtype=np.float32)
         self._check(self._lib.rst_read_geometry(self._ctx, slot, level, out.ctypes.data))
+        return out
+
+    def read_intensity(self, slot: int, level: int) -> np.ndarray:
+        w, h, _, _ = self.level_info(level)
+        out = np.empty((h, w), dtype=np.float32)
+        self._check(self._lib.rst_read_intensity(self._ctx, slot, level, out.ctypes.data))
         return out
 
     def evaluate(self, src_slot: int, dst_slot: int, level: int, T, want_idx: bool = True):

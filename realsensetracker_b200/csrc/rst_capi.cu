@@ -43,6 +43,10 @@ struct rst_ctx {
   size_t depth_bytes[RST_MAX_LEVELS]{};
   float4* d_geom[RST_MAX_LEVELS]{};
   size_t geom_bytes[RST_MAX_LEVELS]{};
+  // photometric term (allocated on first use): RGB staging + intensity pyramid
+  bool photo = false;
+  uint8_t* d_rgb = nullptr;
+  float* d_int[RST_MAX_LEVELS]{};
   bool ext0 = false;  // level 0 read in place from caller memory
   const uint16_t* ext_depth0 = nullptr;
   int ext_pitch0 = 0;
@@ -181,6 +185,8 @@ void rst_ctx_destroy(rst_ctx* c) {
   cudaFree(c->d_pairs); cudaFree(c->d_poses_in); cudaFree(c->d_master); cudaFree(c->d_pose_f32);
   cudaFree(c->d_poses_cm); cudaFree(c->d_stats); cudaFree(c->d_tickets); cudaFree(c->d_partials);
   cudaFree(c->d_idx);
+  cudaFree(c->d_rgb);
+  for (int l = 0; l < RST_MAX_LEVELS; ++l) cudaFree(c->d_int[l]);
   cudaFreeHost(c->h_pairs); cudaFreeHost(c->h_poses); cudaFreeHost(c->h_stats);
   for (auto& r : c->prof_open) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -274,6 +280,7 @@ int32_t rst_begin(rst_ctx* c, int32_t width, int32_t height, const rst_intrinsic
   if (P.num_levels < 1 || P.num_levels > RST_MAX_LEVELS) return fail(c, RST_ERR_INVALID_ARG, "num_levels out of range");
   for (int l = 0; l < P.num_levels; ++l)
     if (P.iters[l] < 0 || P.iters[l] > 10000) return fail(c, RST_ERR_INVALID_ARG, "iters out of range");
+  if (!(P.photo_weight >= 0.f)) return fail(c, RST_ERR_INVALID_ARG, "photo_weight must be >= 0");
   if (!(P.depth_scale > 0.f) || !(P.dist_max > 0.f) || !(P.z_max > P.z_min) || !(intr->fx > 0.f) || !(intr->fy > 0.f))
     return fail(c, RST_ERR_INVALID_ARG, "depth_scale, dist_max, z range and focal lengths must be positive");
   if (P.robust_kind < 0 || P.robust_kind > 2) return fail(c, RST_ERR_INVALID_ARG, "unknown robust_kind");
@@ -321,6 +328,15 @@ int32_t rst_begin(rst_ctx* c, int32_t width, int32_t height, const rst_intrinsic
     c->store_dirty = false;
   }
   c->ext0 = false; c->ext_depth0 = nullptr;
+  c->photo = P.photo_weight > 0.0f;
+  if (c->photo && !c->d_rgb) {
+    RST_CUDA(c, cudaMalloc(&c->d_rgb, (size_t)c->max_w * c->max_h * 3 * c->max_frames));
+    int mw = c->max_w, mh = c->max_h;
+    for (int l = 0; l < RST_MAX_LEVELS; ++l) {
+      RST_CUDA(c, cudaMalloc(&c->d_int[l], (size_t)mw * mh * sizeof(float) * c->max_frames));
+      mw = mw / 2 > 0 ? mw / 2 : 1; mh = mh / 2 > 0 ? mh / 2 : 1;
+    }
+  }
   c->begun = true;
   c->err.clear();
   return RST_OK;
@@ -338,6 +354,13 @@ int32_t rst_upload_frames(rst_ctx* c, const rst_frame* frames, int32_t n, int32_
     if (!f.depth) return fail(c, RST_ERR_INVALID_ARG, "frame.depth is null");
     if (f.width != c->w || f.height != c->h) return fail(c, RST_ERR_INVALID_ARG, "frame size differs from rst_begin");
     if (f.depth_stride_bytes < c->w * 2 || (f.depth_stride_bytes & 1)) return fail(c, RST_ERR_INVALID_ARG, "bad depth stride");
+    if (c->photo && (!f.rgb || f.rgb_stride_bytes < c->w * 3)) return fail(c, RST_ERR_INVALID_ARG, "photo_weight > 0 needs an rgb image in every frame");
+  }
+  if (c->photo) {
+    const size_t fb = (size_t)c->w * c->h * 3;
+    for (int k = 0; k < n; ++k)
+      RST_CUDA(c, cudaMemcpy2DAsync(c->d_rgb + fb * (size_t)(first_slot + k), (size_t)c->w * 3, frames[k].rgb,
+                                    (size_t)frames[k].rgb_stride_bytes, (size_t)c->w * 3, (size_t)c->h, cudaMemcpyHostToDevice, c->stream));
   }
   const size_t dpitch = (size_t)c->pitch[0] * 2;
   int i = 0;
@@ -365,6 +388,7 @@ int32_t rst_set_frames_device(rst_ctx* c, const uint16_t* d_depth, int32_t n, in
   if (first_slot + n > c->max_frames) return fail(c, RST_ERR_CAPACITY, "more frames than the context holds");
   if (row_stride_px < c->w || frame_stride_px < (int64_t)row_stride_px * c->h)
     return fail(c, RST_ERR_INVALID_ARG, "strides smaller than the frame");
+  if (c->photo) return fail(c, RST_ERR_INVALID_ARG, "the photometric term needs host frames with rgb (rst_upload_frames)");
   if (((uintptr_t)d_depth & 15) || (row_stride_px & 7) || (frame_stride_px & 7))
     return fail(c, RST_ERR_ALIGNMENT, "device depth must be 16-byte aligned with row/frame strides multiples of 8 pixels");
   c->ext0 = true;
@@ -380,10 +404,23 @@ static LevelStore level_store(const rst_ctx* c, int l) {
   else { s.depth = c->d_depth[l]; s.depth_pitch = c->pitch[l]; s.depth_frame = c->dframe[l]; }
   s.geom = c->d_geom[l] + kGeomGuard;
   s.geom_frame = c->gframe[l];
+  s.intensity = c->photo ? c->d_int[l] : nullptr;
+  s.int_frame = (int64_t)c->geom[l].w * c->geom[l].h;
   return s;
 }
 
 static int32_t preprocess_impl(rst_ctx* c, int first_slot, int n, bool write_geom) {
+  if (c->photo) {
+    for (int l = 0; l < c->num_levels; ++l) {
+      IntensityArgs ia{};
+      ia.w = c->geom[l].w; ia.h = c->geom[l].h; ia.first_slot = first_slot;
+      ia.out = c->d_int[l]; ia.out_frame = (int64_t)ia.w * ia.h;
+      if (l == 0) { ia.rgb = c->d_rgb; ia.rgb_frame = (int64_t)c->w * c->h * 3; }
+      else { ia.in = c->d_int[l - 1]; ia.in_w = c->geom[l - 1].w; ia.in_frame = (int64_t)c->geom[l - 1].w * c->geom[l - 1].h; }
+      RST_CUDA(c, launch_intensity(ia, n, c->stream));
+      c->launches += 1;
+    }
+  }
   for (int l = 0; l < c->num_levels; ++l) {
     const bool has_next = l + 1 < c->num_levels;
     if (!write_geom && !has_next) break;
@@ -436,6 +473,7 @@ static void fill_icp_args(const rst_ctx* c, int l, IcpArgs* a) {
   a->dmax2 = c->P.dist_max * c->P.dist_max;
   a->ncos_min = c->P.normal_cos_min;
   a->robust_scale = c->P.robust_scale;
+  a->sqrt_lambda = sqrtf(c->P.photo_weight);
   a->pose_master = c->d_master;
   a->pose_f32_out = c->d_pose_f32;
   a->poses_cm = c->d_poses_cm;
@@ -482,7 +520,7 @@ static int32_t pairs_iterate(rst_ctx* c, int first, int n) {
       for (int off = 0; off < n; off += 65535) {
         a.pair_offset = first + off;
         const int cnt = n - off < 65535 ? n - off : 65535;
-        RST_CUDA(c, launch_icp_iter(a, cnt, c->P.robust_kind, ngate, false, c->stream));
+        RST_CUDA(c, launch_icp_iter(a, cnt, c->P.robust_kind, ngate, false, c->photo, c->stream));
         c->launches += 1;
         ++nl;
       }
@@ -765,6 +803,17 @@ int32_t rst_read_geometry(rst_ctx* c, int32_t slot, int32_t level, float* out) {
   return RST_OK;
 }
 
+int32_t rst_read_intensity(rst_ctx* c, int32_t slot, int32_t level, float* out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  if (!c->begun || !c->photo || !out || level < 0 || level >= c->num_levels || slot < 0 || slot >= c->max_frames)
+    return fail(c, RST_ERR_INVALID_ARG, "bad slot/level/out, or the photometric term is off");
+  RST_CUDA(c, cudaSetDevice(c->device));
+  const size_t n = (size_t)c->geom[level].w * c->geom[level].h;
+  RST_CUDA(c, cudaMemcpyAsync(out, c->d_int[level] + n * (size_t)slot, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  RST_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RST_OK;
+}
+
 int32_t rst_evaluate(rst_ctx* c, int32_t src_slot, int32_t dst_slot, int32_t level, const float* pose,
                      int32_t* idx_out, rst_stats* stats_out) {
   if (!c) return RST_ERR_INVALID_ARG;
@@ -792,7 +841,7 @@ int32_t rst_evaluate(rst_ctx* c, int32_t src_slot, int32_t dst_slot, int32_t lev
   a.pair_offset = sp;
   a.update_pose = 0;
   a.idx_out = idx_out ? c->d_idx : nullptr;
-  RST_CUDA(c, launch_icp_iter(a, 1, c->P.robust_kind, c->P.normal_cos_min > -1.0f, idx_out != nullptr, c->stream));
+  RST_CUDA(c, launch_icp_iter(a, 1, c->P.robust_kind, c->P.normal_cos_min > -1.0f, idx_out != nullptr, c->photo, c->stream));
   c->launches += 1;
   RST_CUDA(c, cudaMemcpyAsync(c->h_stats + sp, c->d_stats + sp, sizeof(rst_stats), cudaMemcpyDeviceToHost, c->stream));
   if (idx_out) RST_CUDA(c, cudaMemcpyAsync(idx_out, c->d_idx, npx * 4, cudaMemcpyDeviceToHost, c->stream));

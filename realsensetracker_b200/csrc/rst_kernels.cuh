@@ -60,6 +60,8 @@ struct LevelStore {
   int64_t depth_frame;       // pixels between frames
   float4* geom;              // dense w*h per frame; texel [-1] of every frame is an all-zero guard
   int64_t geom_frame;        // float4 between frames
+  const float* intensity;    // dense w*h per frame (photometric term only), else nullptr
+  int64_t int_frame;
 };
 
 struct PreArgs {
@@ -91,6 +93,7 @@ struct IcpArgs {
   uint32_t d_lo, d_span;      // valid raw depth: (d - d_lo) <= d_span  <=>  d != 0 && z_min <= d*scale <= z_max
   float umax, vmax;           // w - 0.5, h - 0.5
   float depth_scale, dmax2, ncos_min, robust_scale;
+  float sqrt_lambda;          // sqrt(photo_weight), photometric variant only
   /* finalize */
   double* pose_master;        // 12 per pair
   float* pose_f32_out;        // == pose_f32 (written by the last block)
@@ -114,7 +117,19 @@ struct InitArgs {
 
 cudaError_t launch_preprocess(const PreArgs& a, int n_frames, cudaStream_t s);
 cudaError_t launch_icp_iter(const IcpArgs& a, int n_pairs, int robust_kind, bool normal_gate,
-                            bool write_idx, cudaStream_t s);
+                            bool write_idx, bool photo, cudaStream_t s);
+
+/* f2: grey intensity (level 0 from CV_8UC3 RGB, then 2x2 means) */
+struct IntensityArgs {
+  const uint8_t* rgb;        // [frame][h][w][3] dense (level 0 only)
+  const float* in;           // previous level (levels >= 1)
+  float* out;
+  int32_t w, h;              // OUTPUT size
+  int32_t in_w;              // input width (levels >= 1)
+  int64_t in_frame, out_frame, rgb_frame;
+  int32_t first_slot;
+};
+cudaError_t launch_intensity(const IntensityArgs& a, int n_frames, cudaStream_t s);
 cudaError_t launch_init_pairs(const InitArgs& a, cudaStream_t s);
 
 }  // namespace rst
