@@ -311,8 +311,7 @@ int32_t rst_icp3d_depth(rst_ctx* ctx, const rst_frame* frames, int32_t n_frames,
                         float* poses_inout, rst_icp3d_result* results, int32_t* counts_out);
 
 /* Reads back (host xyz_out, n_points x 3) the cloud of one frame of the last rst_icp3d_depth call. */
-int32_t rst_icp3d_read_cloud(rst_ctx* ctx, int32_t frame_index, int32_t width, int32_t height,
-                             int32_t n_frames, float* xyz_out, int32_t n_points);
+int32_t rst_icp3d_read_cloud(rst_ctx* ctx, int32_t frame_index, float* xyz_out, int32_t n_points);
 
 /* Number of kernel launches this context has issued so far (bench evidence). */
 int64_t rst_launch_count(const rst_ctx* ctx);

@@ -123,7 +123,7 @@ def align_lib() -> C.CDLL:
         lib.rst_icp3d_depth.argtypes = [C.c_void_p, P(Frame), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, P(Intrinsics),
                                         C.c_float, C.c_float, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.rst_icp3d_depth.restype = C.c_int32
-        lib.rst_icp3d_read_cloud.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
+        lib.rst_icp3d_read_cloud.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
         lib.rst_icp3d_read_cloud.restype = C.c_int32
         lib.rst_begin.argtypes = [C.c_void_p, C.c_int32, C.c_int32, P(Intrinsics), P(Params)]
         lib.rst_begin.restype = C.c_int32

@@ -172,7 +172,6 @@ class Aligner:
         poses = pose_to_cm(np.broadcast_to(np.eye(4) if T0 is None else T0, (n, 4, 4))).copy()
         res = (N.Icp3dResult * max(n, 1))()
         counts = np.zeros(frames.shape[0], dtype=np.int32)
-        self._icp3d_shape = (frames.shape[2], frames.shape[1], frames.shape[0])
         self._check(self._lib.rst_icp3d_depth(self._ctx, _frames(frames), frames.shape[0], s.ctypes.data, d.ctypes.data, n,
                                               C.byref(K), depth_scale, voxel, max_iter, grid_cell, poses.ctypes.data,
                                               C.addressof(res), counts.ctypes.data))
@@ -180,9 +179,8 @@ class Aligner:
                 np.array([res[i].mean_cost for i in range(n)]), counts)
 
     def icp3d_read_cloud(self, frame_index: int, n_points: int) -> np.ndarray:
-        w, h, nf = self._icp3d_shape
         out = np.empty((n_points, 3), dtype=np.float32)
-        self._check(self._lib.rst_icp3d_read_cloud(self._ctx, frame_index, w, h, nf, out.ctypes.data, n_points))
+        self._check(self._lib.rst_icp3d_read_cloud(self._ctx, frame_index, out.ctypes.data, n_points))
         return out
 
     # ---- staged API ---------------------------------------------------------------------------

@@ -510,6 +510,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_cloudify(const CloudifyDesc* __
 struct Icp3dState {
   void* d_arena = nullptr; size_t d_bytes = 0;
   void* h_arena = nullptr; size_t h_bytes = 0;
+  // layout of the last rst_icp3d_depth call (for rst_icp3d_read_cloud)
+  int last_frames = 0;
+  size_t last_npx = 0, last_cloud_off = 0;
 };
 
 void icp3d_free(void* p) {
@@ -541,6 +544,7 @@ extern "C" int32_t rst_icp3d_pairs(rst_ctx* c, const rst_cloud* src, const rst_c
   void** slot = rst::ctx_ext_slot(c, &free_fn);
   if (!*slot) { *slot = new Icp3dState(); *free_fn = icp3d_free; }
   Icp3dState* st = static_cast<Icp3dState*>(*slot);
+  st->last_frames = 0;  // the arena is about to be re-laid out
 
   // arena layout (same offsets on host staging and device for the uploaded part)
   size_t off = 0;
@@ -687,6 +691,7 @@ extern "C" int32_t rst_icp3d_depth(rst_ctx* c, const rst_frame* frames, int32_t 
     ICP_CUDA(cudaMallocHost(&st->h_arena, download_end));
     st->h_bytes = download_end;
   }
+  st->last_frames = n_frames; st->last_npx = npx; st->last_cloud_off = o_cloud;
   char* H = static_cast<char*>(st->h_arena);
   char* D = static_cast<char*>(st->d_arena);
   CloudifyDesc* cd = reinterpret_cast<CloudifyDesc*>(H + o_cdesc);
@@ -738,24 +743,19 @@ extern "C" int32_t rst_icp3d_depth(rst_ctx* c, const rst_frame* frames, int32_t 
   return RST_OK;
 }
 
-/* Reads back the cloud of frame `frame_index` produced by the last rst_icp3d_depth call (parity tests). */
-extern "C" int32_t rst_icp3d_read_cloud(rst_ctx* c, int32_t frame_index, int32_t width, int32_t height, int32_t n_frames, float* xyz_out,
-                                        int32_t n_points) {
-  if (!c || !xyz_out || frame_index < 0 || frame_index >= n_frames || n_points < 0) return RST_ERR_INVALID_ARG;
+/* Reads back the first n_points points of the cloud of frame `frame_index` produced by the last
+ * rst_icp3d_depth call of this context (parity tests). */
+extern "C" int32_t rst_icp3d_read_cloud(rst_ctx* c, int32_t frame_index, float* xyz_out, int32_t n_points) {
+  if (!c) return RST_ERR_INVALID_ARG;
   void (**free_fn)(void*) = nullptr;
   void** slot = rst::ctx_ext_slot(c, &free_fn);
-  if (!*slot) return RST_ERR_INVALID_ARG;
   Icp3dState* st = static_cast<Icp3dState*>(*slot);
-  // recompute the arena layout of rst_icp3d_depth up to the clouds
-  const size_t npx = (size_t)width * height;
-  size_t off = 0;
-  off = align_up(off + sizeof(CloudifyDesc) * n_frames);
-  CloudifyDesc d;
+  if (!st || !xyz_out || frame_index < 0 || frame_index >= st->last_frames || n_points < 0 || (size_t)n_points > st->last_npx) {
+    rst::ctx_set_error(c, "rst_icp3d_read_cloud: no rst_icp3d_depth result for that frame / bad count");
+    return RST_ERR_INVALID_ARG;
+  }
   if (cudaSetDevice(rst::ctx_device(c)) != cudaSuccess) return RST_ERR_CUDA;
-  if (cudaMemcpy(&d, static_cast<char*>(st->d_arena) + sizeof(CloudifyDesc) * frame_index, sizeof(d), cudaMemcpyDeviceToHost) != cudaSuccess)
-    return RST_ERR_CUDA;
-  if ((size_t)n_points > npx) return RST_ERR_INVALID_ARG;
-  if (cudaMemcpy(xyz_out, d.cloud, sizeof(float) * 3 * (size_t)n_points, cudaMemcpyDeviceToHost) != cudaSuccess) return RST_ERR_CUDA;
-  (void)off;
+  const char* src = static_cast<char*>(st->d_arena) + st->last_cloud_off + st->last_npx * 12 * (size_t)frame_index;
+  if (cudaMemcpy(xyz_out, src, sizeof(float) * 3 * (size_t)n_points, cudaMemcpyDeviceToHost) != cudaSuccess) return RST_ERR_CUDA;
   return RST_OK;
 }

@@ -303,3 +303,32 @@ def test_latency_tiling_matches_oracle_and_is_batch_invariant(seq640):
             al.align_pairs(frames[1:2], frames[0:1], intr, default_params(tiling=7))
     finally:
         al.close()
+
+
+def test_abi_edge_cases_on_the_device(seq_small):
+    """Empty batches, short sequences, non-finite priors: defined behaviour, no crash."""
+    import ctypes as C
+    frames, gt, intr = seq_small
+    n, h, w = frames.shape
+    P = default_params()
+    al = Aligner(w, h, 4, 2)
+    try:
+        lib, ctx = al._lib, al._ctx
+        K = N.Intrinsics(*intr)
+        from realsensetracker_b200.align import _frames
+        poses = np.tile(np.eye(4, dtype=np.float32).reshape(16), (2, 1))
+        assert lib.rst_align_pairs(ctx, _frames(frames[:1]), _frames(frames[:1]), 0, C.byref(K), C.byref(P), poses.ctypes.data, None) == N.RST_OK
+        assert lib.rst_align_sequence(ctx, _frames(frames[:1]), 1, C.byref(K), C.byref(P), poses.ctypes.data, None) == N.RST_OK
+        assert lib.rst_align_pairs(ctx, None, None, 1, C.byref(K), C.byref(P), poses.ctypes.data, None) == N.RST_ERR_INVALID_ARG
+        assert b"null" in lib.rst_last_error(ctx)
+        # a NaN prior: the pair reports NON_FINITE / TOO_FEW instead of poisoning its neighbour in the batch
+        T0 = np.stack([np.eye(4), np.eye(4)])
+        T0[0, 0, 3] = np.nan
+        T, st = al.align_pairs(frames[1:3], frames[0:2], intr, P, T0=T0)
+        assert st[0].status != 0
+        assert st[1].status == 0 and synth.pose_error(T[1], gt[1])[0] < 5e-3
+        # stats are optional
+        assert lib.rst_align_pairs(ctx, _frames(frames[1:2]), _frames(frames[0:1]), 1, C.byref(K), C.byref(P), poses.ctypes.data, None) == N.RST_OK
+        assert al.launch_count > 0
+    finally:
+        al.close()
