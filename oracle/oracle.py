@@ -316,3 +316,89 @@ def align_depth_pairs(src, dst, intr, depth_scale=0.001, voxel=0.05, max_iter=12
                                C.c_float(cy), C.c_float(depth_scale), C.c_float(voxel), C.c_int32(max_iter),
                                C.c_int32(n_threads), T.ctypes.data_as(C.c_void_p), ok.ctypes.data_as(C.c_void_p))
     return ok.astype(bool), np.stack([cm_to_pose(t) for t in T])
+
+
+# ------------------------------------------------------------------ compiled reference (oracle/_ref)
+REF_LIB = HERE / "_ref" / "libref.so"
+REFERENCE_TREE = Path("/root/reference/rs_tracker")
+_ref = None
+
+
+def build_ref() -> Path | None:
+    """Compiles the reference's own align_icp.cpp + point_cloud_utils.cpp (unmodified, from
+    /root/reference) against oracle/shim into oracle/_ref/libref.so. Returns None when the reference
+    tree is not present (GPU box) and no prebuilt library travelled with the snapshot."""
+    if REFERENCE_TREE.exists():
+        res = subprocess.run(["make", "-C", str(HERE), "ref"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("reference build failed:\n" + res.stdout)
+    return REF_LIB if REF_LIB.exists() else None
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        p = build_ref()
+        if p is None:
+            return None
+        _ref = C.CDLL(str(p))
+    return _ref
+
+
+def ref_align_icp3d(src, dst, max_iter=128, T0=None):
+    s, d = _f32(src), _f32(dst)
+    T = pose_to_cm(np.eye(4) if T0 is None else T0)
+    ok = ref_lib().ref_align_icp3d(s.ctypes.data_as(C.c_void_p), C.c_int32(len(s)), d.ctypes.data_as(C.c_void_p),
+                                   C.c_int32(len(d)), C.c_int32(max_iter), T.ctypes.data_as(C.c_void_p))
+    return bool(ok), cm_to_pose(T)
+
+
+def ref_solve_kabsch(src, dst, pairs, weights=None):
+    s, d = _f32(src), _f32(dst)
+    pr = np.ascontiguousarray(pairs, dtype=np.int32)
+    w = _f32(weights) if weights is not None else None
+    T = np.zeros(16, dtype=np.float32)
+    ok = ref_lib().ref_solve_kabsch(s.ctypes.data_as(C.c_void_p), C.c_int32(len(s)), d.ctypes.data_as(C.c_void_p),
+                                    C.c_int32(len(d)), pr.ctypes.data_as(C.c_void_p), C.c_int32(len(pr)),
+                                    w.ctypes.data_as(C.c_void_p) if w is not None else None, T.ctypes.data_as(C.c_void_p))
+    return bool(ok), cm_to_pose(T)
+
+
+def ref_centroid(pts):
+    p = _f32(pts)
+    c = np.zeros(3, dtype=np.float32)
+    ref_lib().ref_centroid(p.ctypes.data_as(C.c_void_p), C.c_int32(len(p)), c.ctypes.data_as(C.c_void_p))
+    return c
+
+
+def ref_remove_nans(pts):
+    p = _f32(pts)
+    out = np.empty_like(p)
+    m = ref_lib().ref_remove_nans(p.ctypes.data_as(C.c_void_p), C.c_int32(len(p)), out.ctypes.data_as(C.c_void_p))
+    return out[:m].copy()
+
+
+def ref_downsample_voxel(pts, voxel):
+    p = _f32(pts)
+    out = np.empty_like(p)
+    m = ref_lib().ref_downsample_voxel(p.ctypes.data_as(C.c_void_p), C.c_int32(len(p)), C.c_float(voxel),
+                                       out.ctypes.data_as(C.c_void_p))
+    return out[:m].copy()
+
+
+def ref_find_correspondences(dst, src):
+    d, s = _f32(dst), _f32(src)
+    idx = np.empty(len(s), dtype=np.int32)
+    d2 = np.empty(len(s), dtype=np.float32)
+    ref_lib().ref_find_correspondences(d.ctypes.data_as(C.c_void_p), C.c_int32(len(d)), s.ctypes.data_as(C.c_void_p),
+                                       C.c_int32(len(s)), idx.ctypes.data_as(C.c_void_p), d2.ctypes.data_as(C.c_void_p))
+    return idx, d2
+
+
+def ref_normals(pts, k=16, viewpoint=(0.0, 0.0, 0.0)):
+    p = _f32(pts)
+    vp = _f32(viewpoint)
+    out = np.empty_like(p)
+    ref_lib().ref_normals(p.ctypes.data_as(C.c_void_p), C.c_int32(len(p)), C.c_int32(k), vp.ctypes.data_as(C.c_void_p),
+                          out.ctypes.data_as(C.c_void_p))
+    return out

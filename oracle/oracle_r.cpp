@@ -7,10 +7,16 @@
  * link or call this file; it is the checker for the cloud-based GPU path and the
  * CPU baseline that bench.py times (`cpu_baseline`, `--impl reference`).
  *
- * PARITY UNPINNED: the reference has no tests / golden vectors / fixtures and
- * cannot be compiled here (needs Eigen3, nanoflann, ChoUtil, fmt — all absent,
- * versions unpinned: `find_package(... REQUIRED)` CMakeLists.txt:11-21). Third-party
- * arithmetic on the path is restated from the published algorithms:
+ * PINNING: the reference has no tests / golden vectors / fixtures, and its real
+ * dependencies (Eigen3, nanoflann, ChoUtil, fmt — versions unpinned, `find_package(...
+ * REQUIRED)` CMakeLists.txt:11-21) are absent, so it cannot be built as shipped. What IS
+ * done: its own align_icp.cpp and point_cloud_utils.cpp are compiled UNMODIFIED from
+ * /root/reference against stand-in headers (oracle/shim, oracle/Makefile target `ref` ->
+ * oracle/_ref/libref.so) and this restatement matches that build BIT FOR BIT on AlignIcp3d
+ * (1..128 iterations), SolveKabsch, ComputeCentroid, RemoveNans, FindCorrespondences and, as
+ * a set, DownsampleVoxel (tests/test_reference_compiled.py). That pins the reference's own
+ * control flow and quirks; the THIRD-PARTY arithmetic stays unpinned and is restated from
+ * the published algorithms on both sides:
  *   - nanoflann KDTreeSingleIndexAdaptor<L2> exact 1-NN (kdtree.hpp:51-57):
  *     result = exact nearest neighbour under fp32 squared L2, accumulated
  *     dx^2+dy^2+dz^2 left to right; any exact search agrees off exact ties.

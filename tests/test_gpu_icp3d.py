@@ -109,3 +109,14 @@ def test_depth_to_cloud_is_bit_exact_and_depth_icp_matches_the_reference_pipelin
     assert counts.tolist() == [160 * 120, 160 * 120]
     cloud = al.icp3d_read_cloud(0, 160 * 120)
     assert np.array_equal(cloud, O.backproject(z, intr)) and (cloud[:40 * 160] == 0).all()
+
+
+@pytest.mark.skipif(O.ref_lib() is None, reason="oracle/_ref/libref.so not present")
+def test_gpu_against_the_compiled_reference_source(al):
+    """The CUDA cloud engine against the reference's own align_icp.cpp (compiled with stand-in headers)."""
+    src, dst = GOLD["src"], GOLD["dst"]
+    for iters in (1, 128):
+        ok_r, T_r = O.ref_align_icp3d(src, dst, iters)
+        ok_g, T_g = al.icp3d_pairs([src], [dst], iters)
+        dt, dr = synth.pose_error(T_g[0], T_r)
+        assert ok_g[0] == ok_r and dt < 1e-4 and dr < 1e-4, (iters, dt, dr)
