@@ -402,3 +402,18 @@ def ref_normals(pts, k=16, viewpoint=(0.0, 0.0, 0.0)):
     ref_lib().ref_normals(p.ctypes.data_as(C.c_void_p), C.c_int32(len(p)), C.c_int32(k), vp.ctypes.data_as(C.c_void_p),
                           out.ctypes.data_as(C.c_void_p))
     return out
+
+
+def ref_align_depth_pairs(src, dst, intr, depth_scale=0.001, voxel=0.05, max_iter=128, n_threads=1):
+    """Batch of depth pairs through the reference's own RemoveNans / DownsampleVoxel / AlignIcp3d."""
+    n, h, w = src.shape
+    s = np.ascontiguousarray(src, dtype=np.uint16)
+    d = np.ascontiguousarray(dst, dtype=np.uint16)
+    fx, fy, cx, cy = intr
+    T = np.tile(pose_to_cm(np.eye(4)), (n, 1))
+    ok = np.zeros(n, dtype=np.int32)
+    ref_lib().ref_align_depth_pairs(s.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), C.c_int32(n), C.c_int32(w),
+                                    C.c_int32(h), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy),
+                                    C.c_float(depth_scale), C.c_float(voxel), C.c_int32(max_iter), C.c_int32(n_threads),
+                                    T.ctypes.data_as(C.c_void_p), ok.ctypes.data_as(C.c_void_p))
+    return ok.astype(bool), np.stack([cm_to_pose(t) for t in T])

@@ -57,6 +57,39 @@ void ref_find_correspondences(const float* dst, int m, const float* src, int n, 
   rs_tracker::FindCorrespondences(tree, s, &i, &q);
   std::memcpy(idx, i.data(), sizeof(int) * n); std::memcpy(d2, q.data(), sizeof(float) * n);
 }
+/* The caller's per-pair sequence (rs_replay_app.cpp:229,246-251) through the reference's own functions:
+ * RemoveNans -> DownsampleVoxel(voxel) x2 -> AlignIcp3d(curr, prev, max_iter). Only the back-projection is
+ * ours (in the reference it happens inside librealsense, rs_driver.cpp:201-202; invalid -> origin, :83-88).
+ * One pair per OpenMP thread. */
+void ref_align_depth_pairs(const unsigned short* src_depth, const unsigned short* dst_depth, int n_pairs, int w, int h,
+                           float fx, float fy, float cx, float cy, float depth_scale, float voxel, int max_iter,
+                           int n_threads, float* T, int* ok) {
+  const size_t npx = (size_t)w * h;
+  auto cloud_of = [&](const unsigned short* d, Cloud3f* out) {
+    Cloud3f raw, clean;
+    raw.SetNumPoints((int)npx);
+    float* p = raw.GetPtr();
+    for (int v = 0; v < h; ++v)
+      for (int u = 0; u < w; ++u, p += 3) {
+        const unsigned short dd = d[(size_t)v * w + u];
+        if (dd == 0) { p[0] = p[1] = p[2] = 0.f; continue; }
+        const float z = (float)dd * depth_scale;
+        p[0] = ((float)u - cx) * z / fx; p[1] = ((float)v - cy) * z / fy; p[2] = z;
+      }
+    rs_tracker::RemoveNans(raw, &clean);
+    if (voxel > 0) rs_tracker::DownsampleVoxel(clean, voxel, out); else *out = clean;
+  };
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
+  for (int i = 0; i < n_pairs; ++i) {
+    Cloud3f s, d;
+    cloud_of(src_depth + npx * i, &s);
+    cloud_of(dst_depth + npx * i, &d);
+    Eigen::Isometry3f x; to_pose(T + 16 * i, &x);
+    ok[i] = rs_tracker::AlignIcp3d(s, d, max_iter, &x) ? 1 : 0;
+    from_pose(x, T + 16 * i);
+  }
+}
+
 void ref_normals(const float* pts, int n, int k, const float* viewpoint, float* out) {
   Cloud3f s, nrm; to_cloud(pts, n, &s);
   const rs_tracker::KDTree3f tree{std::cref(s), 10};

@@ -72,3 +72,16 @@ def test_reference_normals_follow_the_orientation_rule():
     nr = O.ref_normals(pts, k=16)
     assert np.allclose(np.abs(nr @ n), 1.0, atol=1e-3)
     assert ((nr * pts).sum(1) <= 0).all()
+
+
+def test_depth_pipeline_through_the_reference_functions():
+    """back-project -> RemoveNans -> DownsampleVoxel -> AlignIcp3d through the reference's own functions vs Oracle-R:
+    same algorithm, different cloud order after DownsampleVoxel (unordered_map iteration order vs first occurrence),
+    so poses agree to rounding, not bits."""
+    f, intr = GN["frames"], tuple(GN["intr"])
+    ok_r, T_r = O.ref_align_depth_pairs(f[1:3], f[0:2], intr, n_threads=2)
+    ok_o, T_o = O.align_depth_pairs(f[1:3], f[0:2], intr, n_threads=2)
+    assert ok_r.all() and ok_o.all()
+    for i in range(2):
+        dt, dr = synth.pose_error(T_r[i], T_o[i])
+        assert dt < 1e-4 and dr < 1e-4, (dt, dr)
