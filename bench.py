@@ -285,18 +285,26 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         pass
     sampler = ClockSampler(uuid) if rank == 0 else None
 
-    # ---- value: HBM-resident inputs; per-stage events enabled (group boundaries only)
-    al.profile_enable(True)
+    # ---- value: HBM-resident inputs, the library's default schedule (two-stream split of the batch)
     for _ in range(args.warmup):
         with torch.cuda.stream(stream):
             step_resident()
-    al.profile_enable(True)   # reset accumulators after warm-up
     ms_val, launches, t0, t1 = timed(step_resident, args.steps, 0)
-    prof = al.profile_read()
-    al.profile_enable(False)
     clocks = sampler.stop(t0, t1) if sampler else None
     total_pairs = world * n_pairs * args.steps
     value = total_pairs / (ms_val * 1e-3)
+
+    # ---- roofline region: the same steps on ONE stream (stream split off) so that CUDA events around
+    #      each level's launches time the kernels in isolation, not two overlapping halves
+    al.set_stream_split(0)
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            step_resident()
+    al.profile_enable(True)
+    ms_single, _, _, _ = timed(step_resident, args.steps, 0)
+    prof = al.profile_read()
+    al.profile_enable(False)
+    al.set_stream_split(32)
 
     # correctness of what was timed: poses vs ground truth, and (N>1) the gathered block of this rank
     poses_dev = d_poses.cpu().numpy()
@@ -340,6 +348,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         tr = ncu_traffic()
         icp_ms = sum(prof.ms_icp[l] for l in range(3))
         pre_ms = sum(prof.ms_preprocess[l] for l in range(3))
+        ms_val_split, ms_val = ms_val, ms_single   # stage shares refer to the single-stream roofline region
         roofline = {
             "kernel": "k_icp_iter<level 0> (fused association + point-to-plane J^T J / J^T r + reduction + solve)",
             "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -352,7 +361,9 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             "stage_share_of_step": {"icp_l0": prof.ms_icp[0] / ms_val, "icp_l1": prof.ms_icp[1] / ms_val,
                                     "icp_l2": prof.ms_icp[2] / ms_val, "preprocess": pre_ms / ms_val,
                                     "other": max(0.0, 1.0 - (icp_ms + pre_ms) / ms_val)},
+            "measured_in": "single-stream region of the same steps (ms_per_step %.3f); the headline value uses the two-stream split" % (ms_single / args.steps),
         }
+        ms_val = ms_val_split
         # CPU baseline (bounded sample) — rank 0, N=1 only
         cpu = None
         if world == 1 and not args.no_cpu:

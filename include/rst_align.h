@@ -194,6 +194,12 @@ int32_t rst_wait(rst_ctx* ctx, float* poses_out, rst_stats* stats_out);
  * The chunk size never changes results: every pair is reduced in image-size-determined blocks. */
 int32_t rst_set_pipeline_chunk(rst_ctx* ctx, int32_t frames_per_chunk);
 
+/* Batches of at least `min_pairs` pairs (default 32) run their iteration schedule as two halves on two
+ * internal streams, so the launches of one half fill the partial last wave and the latency-bound coarse
+ * levels of the other. min_pairs <= 0 disables the split (single stream; used when timing one kernel in
+ * isolation). Never changes results. */
+int32_t rst_set_stream_split(rst_ctx* ctx, int32_t min_pairs);
+
 /* -------------------------------------------------------------------------
  * Staged / device-resident interface (what the two calls above are built from;
  * this is what an HBM-resident benchmark or a multi-stage host uses).

@@ -70,7 +70,7 @@ ALIGN_SYMBOLS = [
     "rst_params_default", "rst_align_pairs", "rst_align_sequence", "rst_begin", "rst_upload_frames",
     "rst_set_frames_device", "rst_preprocess", "rst_align_slots", "rst_device_results", "rst_sync",
     "rst_level_info", "rst_read_depth", "rst_read_geometry", "rst_read_intensity", "rst_evaluate", "rst_launch_count",
-    "rst_copy_results_device", "rst_profile_enable", "rst_profile_read", "rst_set_pipeline_chunk", "rst_align_pairs_async", "rst_align_sequence_async", "rst_wait", "rst_icp3d_pairs", "rst_icp3d_depth", "rst_icp3d_read_cloud",
+    "rst_copy_results_device", "rst_profile_enable", "rst_profile_read", "rst_set_pipeline_chunk", "rst_set_stream_split", "rst_align_pairs_async", "rst_align_sequence_async", "rst_wait", "rst_icp3d_pairs", "rst_icp3d_depth", "rst_icp3d_read_cloud",
 ]
 
 _align = None
@@ -153,6 +153,8 @@ def align_lib() -> C.CDLL:
         lib.rst_launch_count.restype = C.c_int64
         lib.rst_copy_results_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.rst_copy_results_device.restype = C.c_int32
+        lib.rst_set_stream_split.argtypes = [C.c_void_p, C.c_int32]
+        lib.rst_set_stream_split.restype = C.c_int32
         lib.rst_set_pipeline_chunk.argtypes = [C.c_void_p, C.c_int32]
         lib.rst_set_pipeline_chunk.restype = C.c_int32
         lib.rst_profile_enable.argtypes = [C.c_void_p, C.c_int32]

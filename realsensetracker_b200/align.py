@@ -252,6 +252,9 @@ class Aligner:
                                            idx.ctypes.data if want_idx else None, C.byref(st)))
         return idx, st
 
+    def set_stream_split(self, min_pairs: int):
+        self._check(self._lib.rst_set_stream_split(self._ctx, min_pairs))
+
     def set_pipeline_chunk(self, frames_per_chunk: int):
         self._check(self._lib.rst_set_pipeline_chunk(self._ctx, frames_per_chunk))
 

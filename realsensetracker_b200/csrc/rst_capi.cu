@@ -73,6 +73,7 @@ struct rst_ctx {
 
   cudaStream_t copy_stream = nullptr;   // H2D of the next chunk overlaps compute of the current one
   cudaStream_t work_stream[2] = {nullptr, nullptr};  // chunks alternate between two compute streams
+  int split_min_pairs = 32;             // batches of at least this many pairs iterate as two halves on two streams
   int pipeline_chunk = 0;               // frames (pairs) per upload/compute chunk of the host entry points
   void* ext = nullptr;                  // state of the cloud-based engine (rst_icp3d.cu), created on first use
   void (*ext_free)(void*) = nullptr;
@@ -484,6 +485,20 @@ static void fill_icp_args(const rst_ctx* c, int l, IcpArgs* a) {
   a->idx_out = nullptr;
 }
 
+struct StreamScope {  // kernels/copies issued through the ctx go to `s` while this object lives
+  rst_ctx* c; cudaStream_t saved;
+  StreamScope(rst_ctx* c_, cudaStream_t s) : c(c_), saved(c_->stream) { c->stream = s; }
+  ~StreamScope() { c->stream = saved; }
+};
+
+static int32_t link_streams(rst_ctx* c, cudaStream_t from, cudaStream_t to) {  // `to` waits for `from`
+  cudaEvent_t e = prof_event(c);
+  RST_CUDA(c, cudaEventRecord(e, from));
+  RST_CUDA(c, cudaStreamWaitEvent(to, e, 0));
+  c->ev_pool.push_back(e);  // safe to recycle: the wait is already enqueued
+  return RST_OK;
+}
+
 /* stage 1 of an alignment: pair table + initial poses -> device, state reset */
 static int32_t pairs_begin(rst_ctx* c, const int32_t* src_slots, const int32_t* dst_slots, int32_t n_pairs,
                            const float* poses_in) {
@@ -530,6 +545,23 @@ static int32_t pairs_iterate(rst_ctx* c, int first, int n) {
   return RST_OK;
 }
 
+/* The iteration schedule of a large batch is issued as two halves on the two work streams: the
+ * launches of one half fill the partial last wave (and the latency-bound coarse levels) of the other.
+ * Pairs are independent and reduced in image-size-determined blocks, so the split never changes a bit. */
+static int32_t pairs_iterate_split(rst_ctx* c, int n_pairs) {
+  if (n_pairs < c->split_min_pairs) return pairs_iterate(c, 0, n_pairs);
+  cudaStream_t main_s = c->stream;
+  const int half = (n_pairs + 1) / 2;
+  int32_t rc;
+  for (int k = 0; k < 2; ++k) {
+    if ((rc = link_streams(c, main_s, c->work_stream[k])) != RST_OK) return rc;
+    StreamScope work(c, c->work_stream[k]);
+    if ((rc = pairs_iterate(c, k * half, k == 0 ? half : n_pairs - half)) != RST_OK) return rc;
+  }
+  for (int k = 0; k < 2; ++k) if ((rc = link_streams(c, c->work_stream[k], main_s)) != RST_OK) return rc;
+  return RST_OK;
+}
+
 /* stage 3a: results -> pinned staging, asynchronously on the context stream */
 static int32_t fetch_enqueue(rst_ctx* c, int32_t n_pairs) {
   RST_CUDA(c, cudaMemcpyAsync(c->h_poses, c->d_poses_cm, sizeof(float) * 16 * n_pairs, cudaMemcpyDeviceToHost, c->stream));
@@ -566,8 +598,14 @@ int32_t rst_align_slots(rst_ctx* c, const int32_t* src_slots, const int32_t* dst
   RST_CUDA(c, cudaSetDevice(c->device));
   int32_t rc;
   if ((rc = pairs_begin(c, src_slots, dst_slots, n_pairs, poses_inout)) != RST_OK) return rc;
-  if ((rc = pairs_iterate(c, 0, n_pairs)) != RST_OK) return rc;
+  if ((rc = pairs_iterate_split(c, n_pairs)) != RST_OK) return rc;
   return pairs_fetch(c, n_pairs, poses_inout, stats_out);
+}
+
+int32_t rst_set_stream_split(rst_ctx* c, int32_t min_pairs) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  c->split_min_pairs = min_pairs > 0 ? min_pairs : 0x7fffffff;
+  return RST_OK;
 }
 
 int32_t rst_set_pipeline_chunk(rst_ctx* c, int32_t frames_per_chunk) {
@@ -641,20 +679,6 @@ static int32_t check_frames(rst_ctx* c, const rst_frame* f, int n) {
  * chunk overlap the bandwidth-bound fine-level launches of the other (a single small chunk cannot
  * fill 148 SMs). Results never depend on the chunking: every pair is reduced in blocks fixed by the
  * image size. */
-struct StreamScope {  // kernels/copies issued through the ctx go to `s` while this object lives
-  rst_ctx* c; cudaStream_t saved;
-  StreamScope(rst_ctx* c_, cudaStream_t s) : c(c_), saved(c_->stream) { c->stream = s; }
-  ~StreamScope() { c->stream = saved; }
-};
-
-static int32_t link_streams(rst_ctx* c, cudaStream_t from, cudaStream_t to) {  // `to` waits for `from`
-  cudaEvent_t e = prof_event(c);
-  RST_CUDA(c, cudaEventRecord(e, from));
-  RST_CUDA(c, cudaStreamWaitEvent(to, e, 0));
-  c->ev_pool.push_back(e);  // safe to recycle: the wait is already enqueued
-  return RST_OK;
-}
-
 static int32_t align_pairs_impl(rst_ctx* c, const rst_frame* src, const rst_frame* dst, int32_t n_pairs,
                                 const rst_intrinsics* intr, const rst_params* params, float* poses_inout,
                                 rst_stats* stats_out, bool wait) {
@@ -690,7 +714,7 @@ static int32_t align_pairs_impl(rst_ctx* c, const rst_frame* src, const rst_fram
     StreamScope work(c, ws);
     if ((rc = preprocess_impl(c, p0, n, true)) != RST_OK) return rc;
     if ((rc = preprocess_impl(c, n_pairs + p0, n, ngate)) != RST_OK) return rc;
-    if ((rc = pairs_iterate(c, p0, n)) != RST_OK) return rc;
+    if ((rc = piped ? pairs_iterate(c, p0, n) : pairs_iterate_split(c, n_pairs)) != RST_OK) return rc;
   }
   if (piped)
     for (int k = 0; k < 2; ++k) if ((rc = link_streams(c, c->work_stream[k], main_s)) != RST_OK) return rc;
@@ -744,7 +768,7 @@ static int32_t align_sequence_impl(rst_ctx* c, const rst_frame* frames, int32_t 
     // chunk, pre-processed on the other work stream
     const int p0 = f0 > 0 ? f0 - 1 : 0, p1 = f0 + n - 1;
     if (piped && ci > 0 && (rc = link_streams(c, c->work_stream[(ci - 1) & 1], ws)) != RST_OK) return rc;
-    if ((rc = pairs_iterate(c, p0, p1 - p0)) != RST_OK) return rc;
+    if ((rc = piped ? pairs_iterate(c, p0, p1 - p0) : pairs_iterate_split(c, n_pairs)) != RST_OK) return rc;
   }
   if (piped)
     for (int k = 0; k < 2; ++k) if ((rc = link_streams(c, c->work_stream[k], main_s)) != RST_OK) return rc;
