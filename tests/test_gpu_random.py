@@ -1,0 +1,74 @@
+"""GPU: randomised parity — random smooth surfaces with noise and holes, random sizes (odd widths, tails),
+random poses and parameters. Pyramid / geometry / association must stay bit-exact, normal equations 1e-4."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from realsensetracker_b200 import Aligner, default_params
+from realsensetracker_b200 import _native as N
+
+pytestmark = pytest.mark.gpu
+
+
+def random_depth(rng, w, h):
+    v, u = np.mgrid[0:h, 0:w]
+    z = 1.5 + rng.uniform(0.2, 1.5) * np.sin(u / rng.uniform(15, 60) + rng.uniform(0, 6)) * np.cos(v / rng.uniform(15, 60))
+    z += rng.uniform(-0.5, 0.5) * u / w + rng.uniform(-0.5, 0.5) * v / h
+    z += rng.normal(scale=rng.choice([0.0, 0.002, 0.01]), size=z.shape)
+    if rng.random() < 0.5:                                   # a depth step (occlusion boundary)
+        z[:, rng.integers(w // 4, 3 * w // 4):] += rng.uniform(0.3, 1.0)
+    d = np.clip(np.round(z / 0.001), 0, 65535).astype(np.uint16)
+    d[rng.random(d.shape) < rng.choice([0.0, 0.05, 0.3])] = 0
+    for _ in range(rng.integers(0, 4)):
+        y, x = rng.integers(0, h - 8), rng.integers(0, w - 8)
+        d[y:y + rng.integers(2, 8), x:x + rng.integers(2, 8)] = 0
+    return d
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_inputs_stay_bit_exact(seed):
+    rng = np.random.default_rng(1000 + seed)
+    w, h = int(rng.integers(40, 300)), int(rng.integers(40, 200))
+    f = rng.uniform(0.5, 1.2) * w
+    intr = (float(f), float(f * rng.uniform(0.9, 1.1)), float(w / 2 + rng.uniform(-5, 5)), float(h / 2 + rng.uniform(-5, 5)))
+    levels = 3 if min(w, h) >= 64 else 2
+    kw = dict(num_levels=levels, z_min=float(rng.choice([0.1, 1.0])), z_max=float(rng.choice([2.5, 10.0])),
+              dist_max=float(rng.choice([0.05, 0.2, 1.0])), normal_depth_tol=float(rng.choice([0.01, 0.05, 0.2])),
+              pyr_depth_tol=int(rng.choice([0, 30, 100, 5000])),
+              robust_kind=int(rng.choice([0, 1, 2])), robust_scale=float(rng.choice([0.005, 0.05])),
+              normal_cos_min=float(rng.choice([-2.0, 0.5, 0.95])), tiling=int(rng.choice([0, 1])))
+    P, Po = default_params(**kw), O.default_params(**kw)
+    frames = np.stack([random_depth(rng, w, h) for _ in range(2)])
+    ang = rng.normal(size=3) * rng.choice([0.0, 0.01, 0.1])
+    from realsensetracker_b200 import synth
+    T = synth.make_pose(synth.rotvec_to_R(ang), rng.normal(size=3) * rng.choice([0.0, 0.01, 0.1]))
+    T = T.astype(np.float32).astype(np.float64)
+    al = Aligner(w, h, 2, 1)
+    try:
+        al.begin(w, h, intr, P)
+        al.upload(frames)
+        al.preprocess(0, 2)
+        ds, dd = frames[1], frames[0]
+        for l in range(levels):
+            L = O.level_info(intr, w, h, l)
+            if l > 0:
+                ds, dd = O.pyr_down(ds, Po.pyr_depth_tol), O.pyr_down(dd, Po.pyr_depth_tol)
+            assert np.array_equal(al.read_depth(1, l), ds) and np.array_equal(al.read_depth(0, l), dd)
+            Gd, Gs = O.geometry(dd, L, Po), O.geometry(ds, L, Po)
+            assert np.array_equal(al.read_geometry(0, l).view(np.uint32), Gd.view(np.uint32)), (seed, l, "geometry")
+            use_ng = Po.normal_cos_min > -1.0
+            idx_o, st_o = O.evaluate(ds, Gs if use_ng else None, Gd, L, Po, T)
+            idx_g, st_g = al.evaluate(1, 0, l, T)
+            assert np.array_equal(idx_g, idx_o), (seed, l, int((idx_g != idx_o).sum()))
+            assert st_g.count == st_o.count
+            if st_o.count > 50:
+                Ao, Ag = np.array(st_o.A[:]), np.array(st_g.A[:])
+                assert np.max(np.abs(Ag - Ao)) <= 1e-4 * np.max(np.abs(Ao)), (seed, l)
+                assert abs(st_g.sum_wr2 - st_o.sum_wr2) <= 1e-4 * st_o.sum_wr2 + 1e-12
+        # the full loop never crashes and reports a status consistent with the oracle's
+        Tg, st = al.align_pairs(frames[1:2], frames[0:1], intr, P, T0=T)
+        To, so = O.align_pair(frames[1], frames[0], intr, Po, T0=T)
+        assert (st[0].status == 0) == (so.status == 0) or st[0].count < 200
+        assert np.isfinite(Tg).all()
+    finally:
+        al.close()
