@@ -60,6 +60,34 @@ void PoseError(const Mat4d& est, const Mat4d& gt, double* t_err, double* r_err) 
 }
 }  // namespace
 
+// minimal stand-in for the reference's Cloud3f accessors (cho::core::PointCloud<float,3>)
+struct VecCloud {
+  std::vector<float> xyz;
+  const float* GetPtr() const { return xyz.data(); }
+  int GetNumPoints() const { return static_cast<int>(xyz.size() / 3); }
+};
+
+// the pairwise path of rs_align_app.cpp:295-303 on clouds: SolveKabsch from known matches, then AlignIcp3d
+static bool CloudSelfTest(rs_tracker::AlignContext& ctx) {
+  VecCloud src, dst;
+  unsigned s = 12345u;
+  auto rnd = [&]() { s = s * 1664525u + 1013904223u; return (float)((s >> 8) & 0xFFFF) / 32768.0f - 1.0f; };
+  const float c = std::cos(0.05f), sn = std::sin(0.05f);
+  std::vector<std::pair<int, int>> idx;
+  for (int i = 0; i < 500; ++i) {
+    const float x = rnd(), y = rnd(), z = rnd();
+    src.xyz.insert(src.xyz.end(), {x, y, z});
+    dst.xyz.insert(dst.xyz.end(), {c * x - sn * y + 0.05f, sn * x + c * y - 0.03f, z + 0.02f});  // R_z(0.05), t
+    idx.emplace_back(i, i);
+  }
+  rs_tracker::Pose xfm;
+  if (!rs_tracker::SolveKabsch(ctx, src, dst, idx, {}, &xfm)) return false;
+  float mean_cost = 0.f;
+  if (!rs_tracker::AlignIcp3d(ctx, src, dst, 32, &xfm, &mean_cost)) return false;
+  std::printf("cloud self-test: R01 %.5f (want %.5f), t = %.4f %.4f %.4f, mean cost %.2e\n", xfm(0, 1), -sn, xfm(0, 3), xfm(1, 3), xfm(2, 3), mean_cost);
+  return std::fabs(xfm(0, 1) + sn) < 1e-4f && std::fabs(xfm(0, 3) - 0.05f) < 1e-4f && std::fabs(xfm(2, 3) - 0.02f) < 1e-4f;
+}
+
 int main(int argc, char** argv) {
   const int n_frames = argc > 1 ? std::atoi(argv[1]) : 20;
   const int w = 640, h = 480;
@@ -69,6 +97,7 @@ int main(int argc, char** argv) {
 
   rs_tracker::AlignContext ctx(/*device=*/0, w, h, /*max_frames=*/2, /*max_pairs=*/1);
   rs_tracker::AlignParams params;
+  if (!CloudSelfTest(ctx)) { std::printf("cloud self-test FAILED\n"); return 2; }
 
   std::vector<std::uint16_t> prev(w * h), curr(w * h);
   Mat4d total{};  // accumulated estimate: camera k -> camera 0

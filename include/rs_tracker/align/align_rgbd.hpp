@@ -20,6 +20,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "rst_align.h"
@@ -148,6 +149,37 @@ inline bool AlignSequence(AlignContext& ctx, const std::vector<DepthFrame>& fram
   for (const auto& x : st) ok = ok && x.status == RST_STATUS_OK;
   if (stats) *stats = std::move(st);
   return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cloud-based calls with the reference's own algorithm (align_icp.hpp:14-24), on the GPU.
+// `Cloud` is any type with GetPtr() -> const float* (xyz interleaved) and GetNumPoints() — the
+// reference's Cloud3f = cho::core::PointCloud<float,3> qualifies as is (rs_viewer.cpp:91-92).
+// ------------------------------------------------------------------------------------------------
+
+/// bool AlignIcp3d(src, dst, max_iter, &transform)  align_icp.hpp:22-24 / align_icp.cpp:73-167.
+template <class Cloud>
+inline bool AlignIcp3d(AlignContext& ctx, const Cloud& src, const Cloud& dst, const int max_iter, Pose* const transform,
+                       float* const mean_cost = nullptr) {
+  const rst_cloud s{src.GetPtr(), static_cast<std::int32_t>(src.GetNumPoints())};
+  const rst_cloud d{dst.GetPtr(), static_cast<std::int32_t>(dst.GetNumPoints())};
+  rst_icp3d_result res{};
+  const int rc = rst_icp3d_pairs(ctx.get(), &s, &d, 1, max_iter, /*grid_cell=*/0.f, transform->m.data(), &res, nullptr, nullptr);
+  if (mean_cost) *mean_cost = res.mean_cost;
+  return rc == RST_OK && res.ok != 0;
+}
+
+/// bool SolveKabsch(src, dst, indices, weights, &xfm)  align_icp.hpp:14-18 / align_icp.cpp:18-71.
+template <class Cloud>
+inline bool SolveKabsch(AlignContext& ctx, const Cloud& src, const Cloud& dst, const std::vector<std::pair<int, int>>& indices,
+                        const std::vector<float>& weights, Pose* const xfm) {
+  static_assert(sizeof(std::pair<int, int>) == 2 * sizeof(std::int32_t), "pair<int,int> must be two packed int32");
+  const rst_cloud s{src.GetPtr(), static_cast<std::int32_t>(src.GetNumPoints())};
+  const rst_cloud d{dst.GetPtr(), static_cast<std::int32_t>(dst.GetNumPoints())};
+  std::int32_t ok = 0;
+  const int rc = rst_solve_kabsch(ctx.get(), &s, &d, indices.empty() ? nullptr : &indices[0].first, static_cast<std::int32_t>(indices.size()),
+                                  weights.empty() ? nullptr : weights.data(), xfm->m.data(), &ok);
+  return rc == RST_OK && ok != 0;
 }
 
 #ifdef RS_TRACKER_HAVE_EIGEN

@@ -304,6 +304,14 @@ int32_t rst_icp3d_pairs(rst_ctx* ctx, const rst_cloud* src, const rst_cloud* dst
                         int32_t max_iter, float grid_cell, float* poses_inout,
                         rst_icp3d_result* results, int32_t* nbrs_out, float* weights_out);
 
+/* bool SolveKabsch(src, dst, indices, weights, &xfm)  (align_icp.hpp:14-18, align_icp.cpp:18-71) on the device:
+ * closed-form pose from GIVEN (src index, dst index) pairs — the initialiser rs_align_app.cpp:295 feeds to
+ * AlignIcp3d. `pairs`: n_pairs x 2 int32; `weights`: n_pairs floats or NULL (the reference's empty vector);
+ * unweighted centroids, weighted covariance, exactly as written there. pose_out: 16 floats column-major;
+ * *ok_out = 0 (and RST_OK) when either cloud has fewer than 3 points (:23-25). All pointers are HOST memory. */
+int32_t rst_solve_kabsch(rst_ctx* ctx, const rst_cloud* src, const rst_cloud* dst, const int32_t* pairs,
+                         int32_t n_pairs, const float* weights, float* pose_out, int32_t* ok_out);
+
 /* The reference caller's whole per-pair sequence on the device, from depth frames
  * (rs_replay_app.cpp:229,246-251): back-projection with invalid pixels at the origin
  * (rs_driver.cpp:83-88,201-202) -> RemoveNans -> DownsampleVoxel(voxel) (first point per voxel, in

@@ -161,6 +161,18 @@ class Aligner:
             o += m
         return ok, T, out
 
+    def solve_kabsch(self, src, dst, pairs, weights=None):
+        """SolveKabsch(src, dst, indices, weights, &xfm) (align_icp.cpp:18-71) on the GPU. Returns (ok, pose 4x4)."""
+        S, D = np.ascontiguousarray(src, dtype=np.float32), np.ascontiguousarray(dst, dtype=np.float32)
+        pr = np.ascontiguousarray(pairs, dtype=np.int32)
+        w = np.ascontiguousarray(weights, dtype=np.float32) if weights is not None else None
+        cs, cd = N.Cloud(S.ctypes.data, len(S)), N.Cloud(D.ctypes.data, len(D))
+        pose = np.zeros(16, dtype=np.float32)
+        ok = C.c_int32(0)
+        self._check(self._lib.rst_solve_kabsch(self._ctx, C.byref(cs), C.byref(cd), pr.ctypes.data, len(pr),
+                                               w.ctypes.data if w is not None else None, pose.ctypes.data, C.byref(ok)))
+        return bool(ok.value), cm_to_pose(pose)
+
     def icp3d_depth(self, frames: np.ndarray, src_idx, dst_idx, intr, depth_scale: float = 0.001, voxel: float = 0.05,
                     max_iter: int = 128, T0=None, grid_cell: float = 0.1):
         """The reference caller's per-pair sequence from depth frames (rs_replay_app.cpp:229,246-251), on the GPU.

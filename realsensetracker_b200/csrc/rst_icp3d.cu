@@ -506,6 +506,52 @@ __global__ void __launch_bounds__(kThreads, 1) k_cloudify(const CloudifyDesc* __
   (void)s_base;
 }
 
+// ----------------------------------------------------------------------------------------------
+// SolveKabsch (align_icp.cpp:18-71): closed-form pose from GIVEN index pairs, optional weights.
+// Centroids over the pairs are unweighted (:28-35); the covariance is the fp32 outer product cast to
+// double, multiplied by the weight in double (:46-56); then the same SVD / reflection patch /
+// quaternion round trip as AlignIcp3d. One block.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) k_kabsch(const float* __restrict__ src, const float* __restrict__ dst,
+                                                        const int2* __restrict__ pairs, int n_pairs,
+                                                        const float* __restrict__ weights, float* __restrict__ pose_out) {
+  __shared__ double s_part[kWarps][16];
+  __shared__ double s_sum[16];
+  const int tid = threadIdx.x;
+  double m6[6] = {0, 0, 0, 0, 0, 0};
+  for (int c = tid; c < n_pairs; c += kThreads) {
+    const int2 p = pairs[c];
+    for (int a = 0; a < 3; ++a) { m6[a] += (double)src[3 * p.x + a]; m6[3 + a] += (double)dst[3 * p.y + a]; }
+  }
+  block_sum<6>(m6, s_part, s_sum);
+  float sm[3], dm[3];
+  for (int a = 0; a < 3; ++a) { sm[a] = (float)s_sum[a] / (float)n_pairs; dm[a] = (float)s_sum[3 + a] / (float)n_pairs; }
+  __syncthreads();
+  double cv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int c = tid; c < n_pairs; c += kThreads) {
+    const int2 p = pairs[c];
+    const double w = weights ? (double)weights[c] : 1.0;
+    float d[3], s3[3];
+    for (int a = 0; a < 3; ++a) { d[a] = subrn(dst[3 * p.y + a], dm[a]); s3[a] = subrn(src[3 * p.x + a], sm[a]); }
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) cv[3 * a + b] += w * (double)mulrn(d[a], s3[b]);
+  }
+  block_sum<9>(cv, s_part, s_sum);
+  if (tid == 0) {
+    double cov[9], uvt[9];
+    for (int k = 0; k < 9; ++k) cov[k] = s_sum[k];
+    svd_uvt(cov, uvt);
+    float R[9], t[3];
+    for (int k = 0; k < 9; ++k) R[k] = (float)uvt[k];
+    const float det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
+    if (det < 0) { R[2] *= -1; R[5] *= -1; R[8] *= -1; }  // :61-63
+    for (int a = 0; a < 3; ++a) t[a] = dm[a] - (R[3 * a] * sm[0] + R[3 * a + 1] * sm[1] + R[3 * a + 2] * sm[2]);  // :66
+    float T[16];
+    compose_pose(R, t, T);  // :69
+    for (int k = 0; k < 16; ++k) pose_out[k] = T[k];
+  }
+}
+
 /* grow-only device/pinned arenas of the cloud engine, owned by the context */
 struct Icp3dState {
   void* d_arena = nullptr; size_t d_bytes = 0;
@@ -757,5 +803,70 @@ extern "C" int32_t rst_icp3d_read_cloud(rst_ctx* c, int32_t frame_index, float* 
   if (cudaSetDevice(rst::ctx_device(c)) != cudaSuccess) return RST_ERR_CUDA;
   const char* src = static_cast<char*>(st->d_arena) + st->last_cloud_off + st->last_npx * 12 * (size_t)frame_index;
   if (cudaMemcpy(xyz_out, src, sizeof(float) * 3 * (size_t)n_points, cudaMemcpyDeviceToHost) != cudaSuccess) return RST_ERR_CUDA;
+  return RST_OK;
+}
+
+/* SolveKabsch(src, dst, indices, weights, &xfm)  align_icp.cpp:18-71 on the device. pairs: n_pairs x
+ * (src index, dst index), weights nullable (= empty vector), all HOST pointers; pose_out: 16 floats,
+ * column-major. Returns RST_OK and *ok_out = 0 for < 3 points in either cloud (:23-25). */
+extern "C" int32_t rst_solve_kabsch(rst_ctx* c, const rst_cloud* src, const rst_cloud* dst, const int32_t* pairs, int32_t n_pairs,
+                                    const float* weights, float* pose_out, int32_t* ok_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  auto fail = [&](int code, const std::string& m) { rst::ctx_set_error(c, m); return code; };
+  if (!src || !dst || !pose_out || !ok_out || n_pairs < 0 || (n_pairs > 0 && !pairs)) return fail(RST_ERR_INVALID_ARG, "null argument");
+  *ok_out = 0;
+  if (src->n < 3 || dst->n < 3) return RST_OK;
+  if (n_pairs == 0) return fail(RST_ERR_INVALID_ARG, "no index pairs");
+  for (int i = 0; i < n_pairs; ++i)
+    if (pairs[2 * i] < 0 || pairs[2 * i] >= src->n || pairs[2 * i + 1] < 0 || pairs[2 * i + 1] >= dst->n)
+      return fail(RST_ERR_INVALID_ARG, "pair index out of range");
+#define ICP_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess) return fail(RST_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+  ICP_CUDA(cudaSetDevice(rst::ctx_device(c)));
+  cudaStream_t stream = rst::ctx_stream(c);
+  void (**free_fn)(void*) = nullptr;
+  void** slot = rst::ctx_ext_slot(c, &free_fn);
+  if (!*slot) { *slot = new Icp3dState(); *free_fn = icp3d_free; }
+  Icp3dState* st = static_cast<Icp3dState*>(*slot);
+  st->last_frames = 0;
+  size_t off = 0;
+  const size_t o_pose = off; off = align_up(off + 64);
+  const size_t o_src = off; off = align_up(off + sizeof(float) * 3 * (size_t)src->n);
+  const size_t o_dst = off; off = align_up(off + sizeof(float) * 3 * (size_t)dst->n);
+  const size_t o_pairs = off; off = align_up(off + sizeof(int2) * (size_t)n_pairs);
+  const size_t o_w = off; off = align_up(off + sizeof(float) * (size_t)n_pairs);
+  const size_t total = off;
+  if (st->d_bytes < total) {
+    ICP_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(st->d_arena); st->d_arena = nullptr; st->d_bytes = 0;
+    ICP_CUDA(cudaMalloc(&st->d_arena, total));
+    st->d_bytes = total;
+  }
+  if (st->h_bytes < total) {
+    ICP_CUDA(cudaStreamSynchronize(stream));
+    cudaFreeHost(st->h_arena); st->h_arena = nullptr; st->h_bytes = 0;
+    ICP_CUDA(cudaMallocHost(&st->h_arena, total));
+    st->h_bytes = total;
+  }
+  char* H = static_cast<char*>(st->h_arena);
+  char* D = static_cast<char*>(st->d_arena);
+  std::memcpy(H + o_src, src->xyz, sizeof(float) * 3 * (size_t)src->n);
+  std::memcpy(H + o_dst, dst->xyz, sizeof(float) * 3 * (size_t)dst->n);
+  std::memcpy(H + o_pairs, pairs, sizeof(int2) * (size_t)n_pairs);
+  if (weights) std::memcpy(H + o_w, weights, sizeof(float) * (size_t)n_pairs);
+  ICP_CUDA(cudaMemcpyAsync(D + o_src, H + o_src, total - o_src, cudaMemcpyHostToDevice, stream));
+  k_kabsch<<<1, kThreads, 0, stream>>>(reinterpret_cast<const float*>(D + o_src), reinterpret_cast<const float*>(D + o_dst),
+                                       reinterpret_cast<const int2*>(D + o_pairs), n_pairs,
+                                       weights ? reinterpret_cast<const float*>(D + o_w) : nullptr, reinterpret_cast<float*>(D + o_pose));
+  ICP_CUDA(cudaGetLastError());
+  rst::ctx_count_launches(c, 1);
+  ICP_CUDA(cudaMemcpyAsync(H + o_pose, D + o_pose, 64, cudaMemcpyDeviceToHost, stream));
+  ICP_CUDA(cudaStreamSynchronize(stream));
+  std::memcpy(pose_out, H + o_pose, 64);
+  *ok_out = 1;
+#undef ICP_CUDA
   return RST_OK;
 }

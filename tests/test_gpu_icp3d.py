@@ -120,3 +120,22 @@ def test_gpu_against_the_compiled_reference_source(al):
         ok_g, T_g = al.icp3d_pairs([src], [dst], iters)
         dt, dr = synth.pose_error(T_g[0], T_r)
         assert ok_g[0] == ok_r and dt < 1e-4 and dr < 1e-4, (iters, dt, dr)
+
+
+def test_solve_kabsch_on_the_device(al):
+    """rst_solve_kabsch vs Oracle-R (and, through it, the compiled reference): align_icp.cpp:18-71."""
+    src, dst = GOLD["src"], GOLD["dst_big"]
+    rng = np.random.default_rng(4)
+    pairs = np.stack([np.arange(len(src)), np.arange(len(src))], 1)[rng.permutation(len(src))[:400]]
+    for w in (None, GOLD["kabsch_w"][:400]):
+        ok_o, T_o = O.solve_kabsch(src, dst, pairs, w)
+        ok_g, T_g = al.solve_kabsch(src, dst, pairs, w)
+        dt, dr = synth.pose_error(T_g, T_o)
+        assert ok_g and ok_o and dt < 1e-5 and dr < 1e-5, (dt, dr)
+        assert synth.pose_error(T_g, GOLD["T_big"]) < (1e-4, 1e-4)          # the known rotation of rs_align_app.cpp:257-263
+    ok_g, _ = al.solve_kabsch(src[:2], dst, pairs[:1] * 0)
+    assert ok_g is False                                                     # < 3 points (:23-25)
+    # Kabsch initialiser -> AlignIcp3d, the order rs_align_app.cpp:295-303 uses
+    ok_k, T_k = al.solve_kabsch(src, dst, pairs)
+    ok_i, T_i = al.icp3d_pairs([src], [dst], 16, T0=T_k)
+    assert ok_i[0] and synth.pose_error(T_i[0], GOLD["T_big"]) < (1e-4, 1e-4)
