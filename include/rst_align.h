@@ -312,6 +312,13 @@ int32_t rst_icp3d_pairs(rst_ctx* ctx, const rst_cloud* src, const rst_cloud* dst
 int32_t rst_solve_kabsch(rst_ctx* ctx, const rst_cloud* src, const rst_cloud* dst, const int32_t* pairs,
                          int32_t n_pairs, const float* weights, float* pose_out, int32_t* ok_out);
 
+/* ComputeNormals(cloud, tree, k, &normals) + OrientNormals(cloud, viewpoint, &normals)
+ * (point_cloud_utils.cpp:176-216) on the device: exact k nearest neighbours (k in [2,32], counting the
+ * point itself; rs_align_app.cpp:25 uses 16), fp32 centroid + covariance, eigenvector of the smallest
+ * eigenvalue, flipped so that n . (p - viewpoint) <= 0. normals_out: n x 3 floats. HOST pointers. */
+int32_t rst_cloud_normals(rst_ctx* ctx, const rst_cloud* cloud, int32_t k, const float* viewpoint,
+                          float grid_cell, float* normals_out);
+
 /* The reference caller's whole per-pair sequence on the device, from depth frames
  * (rs_replay_app.cpp:229,246-251): back-projection with invalid pixels at the origin
  * (rs_driver.cpp:83-88,201-202) -> RemoveNans -> DownsampleVoxel(voxel) (first point per voxel, in

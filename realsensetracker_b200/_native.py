@@ -70,7 +70,7 @@ ALIGN_SYMBOLS = [
     "rst_params_default", "rst_align_pairs", "rst_align_sequence", "rst_begin", "rst_upload_frames",
     "rst_set_frames_device", "rst_preprocess", "rst_align_slots", "rst_device_results", "rst_sync",
     "rst_level_info", "rst_read_depth", "rst_read_geometry", "rst_read_intensity", "rst_evaluate", "rst_launch_count",
-    "rst_copy_results_device", "rst_profile_enable", "rst_profile_read", "rst_set_pipeline_chunk", "rst_set_stream_split", "rst_align_pairs_async", "rst_align_sequence_async", "rst_wait", "rst_icp3d_pairs", "rst_solve_kabsch", "rst_icp3d_depth", "rst_icp3d_read_cloud",
+    "rst_copy_results_device", "rst_profile_enable", "rst_profile_read", "rst_set_pipeline_chunk", "rst_set_stream_split", "rst_align_pairs_async", "rst_align_sequence_async", "rst_wait", "rst_icp3d_pairs", "rst_solve_kabsch", "rst_cloud_normals", "rst_icp3d_depth", "rst_icp3d_read_cloud",
 ]
 
 _align = None
@@ -122,6 +122,8 @@ def align_lib() -> C.CDLL:
         lib.rst_icp3d_pairs.restype = C.c_int32
         lib.rst_solve_kabsch.argtypes = [C.c_void_p, P(Cloud), P(Cloud), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, P(C.c_int32)]
         lib.rst_solve_kabsch.restype = C.c_int32
+        lib.rst_cloud_normals.argtypes = [C.c_void_p, P(Cloud), C.c_int32, C.c_void_p, C.c_float, C.c_void_p]
+        lib.rst_cloud_normals.restype = C.c_int32
         lib.rst_icp3d_depth.argtypes = [C.c_void_p, P(Frame), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, P(Intrinsics),
                                         C.c_float, C.c_float, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.rst_icp3d_depth.restype = C.c_int32

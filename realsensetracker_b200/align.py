@@ -173,6 +173,15 @@ class Aligner:
                                                w.ctypes.data if w is not None else None, pose.ctypes.data, C.byref(ok)))
         return bool(ok.value), cm_to_pose(pose)
 
+    def cloud_normals(self, cloud, k: int = 16, viewpoint=(0.0, 0.0, 0.0), grid_cell: float = 0.0) -> np.ndarray:
+        """ComputeNormals + OrientNormals (point_cloud_utils.cpp:176-216) on the GPU: [n,3] float32 normals."""
+        S = np.ascontiguousarray(cloud, dtype=np.float32)
+        vp = np.ascontiguousarray(viewpoint, dtype=np.float32)
+        out = np.empty_like(S)
+        cs = N.Cloud(S.ctypes.data, len(S))
+        self._check(self._lib.rst_cloud_normals(self._ctx, C.byref(cs), k, vp.ctypes.data, grid_cell, out.ctypes.data))
+        return out
+
     def icp3d_depth(self, frames: np.ndarray, src_idx, dst_idx, intr, depth_scale: float = 0.001, voxel: float = 0.05,
                     max_iter: int = 128, T0=None, grid_cell: float = 0.1):
         """The reference caller's per-pair sequence from depth frames (rs_replay_app.cpp:229,246-251), on the GPU.

@@ -552,6 +552,186 @@ __global__ void __launch_bounds__(kThreads, 1) k_kabsch(const float* __restrict_
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// ComputeNormals + OrientNormals (point_cloud_utils.cpp:176-216) on the device: for every point the
+// exact k nearest neighbours (k includes the point itself, :184), fp32 centroid and covariance summed
+// in ascending-distance order (:187-198), eigenvector of the smallest eigenvalue of the 3x3 covariance
+// (SelfAdjointEigenSolver, :201-202; here a cyclic Jacobi in fp32), flipped so that
+// n . (p - viewpoint) <= 0 (:210-214). One block per cloud: the grid of the cloud is built exactly as
+// for the ICP, then each thread owns points tid, tid + 1024, ...
+// ----------------------------------------------------------------------------------------------
+constexpr int kMaxK = 32;
+
+struct NormalsDesc {
+  const float* pts; int n;
+  int* cell_start; int* cell_fill; float4* sorted;
+  float* normals;   // n x 3 out
+};
+
+// k nearest neighbours of p by ring expansion; (d2, index) kept sorted ascending, ties to the lower index
+__device__ void knn_search(const Grid& g, const int* __restrict__ cell_start, const float4* __restrict__ sorted, float px, float py,
+                           float pz, int k, float* bd, int* bj) {
+  const int cx = cell_coord(px, g.lox, g.inv_h, g.nx), cy = cell_coord(py, g.loy, g.inv_h, g.ny), cz = cell_coord(pz, g.loz, g.inv_h, g.nz);
+  int cnt = 0;
+  for (int r = 0;; ++r) {
+    const int x0 = max(cx - r, 0), x1 = min(cx + r, g.nx - 1);
+    const int y0 = max(cy - r, 0), y1 = min(cy + r, g.ny - 1);
+    const int z0 = max(cz - r, 0), z1 = min(cz + r, g.nz - 1);
+    for (int z = z0; z <= z1; ++z)
+      for (int y = y0; y <= y1; ++y) {
+        const bool inner_zy = (abs(z - cz) < r) && (abs(y - cy) < r);
+        for (int x = x0; x <= x1; ++x) {
+          if (inner_zy && abs(x - cx) < r) { x = cx + r - 1; continue; }
+          const int c = (z * g.ny + y) * g.nx + x;
+          const int e = cell_start[c + 1];
+          for (int q = cell_start[c]; q < e; ++q) {
+            const float4 v = sorted[q];
+            const float dx = subrn(px, v.x), dy = subrn(py, v.y), dz = subrn(pz, v.z);
+            const float d2 = addrn(addrn(mulrn(dx, dx), mulrn(dy, dy)), mulrn(dz, dz));
+            const int j = __float_as_int(v.w);
+            if (cnt == k && !(d2 < bd[k - 1] || (d2 == bd[k - 1] && j < bj[k - 1]))) continue;
+            int i = cnt < k ? cnt : k - 1;   // insertion, as nanoflann's KNNResultSet
+            for (; i > 0 && (bd[i - 1] > d2 || (bd[i - 1] == d2 && bj[i - 1] > j)); --i) { bd[i] = bd[i - 1]; bj[i] = bj[i - 1]; }
+            bd[i] = d2; bj[i] = j;
+            if (cnt < k) ++cnt;
+          }
+        }
+      }
+    if (x0 == 0 && x1 == g.nx - 1 && y0 == 0 && y1 == g.ny - 1 && z0 == 0 && z1 == g.nz - 1) break;
+    if (cnt < k) continue;
+    float bound = FLT_MAX;
+    if (cx - r > 0) bound = fminf(bound, px - (g.lox + (float)(cx - r) * g.h));
+    if (cx + r < g.nx - 1) bound = fminf(bound, (g.lox + (float)(cx + r + 1) * g.h) - px);
+    if (cy - r > 0) bound = fminf(bound, py - (g.loy + (float)(cy - r) * g.h));
+    if (cy + r < g.ny - 1) bound = fminf(bound, (g.loy + (float)(cy + r + 1) * g.h) - py);
+    if (cz - r > 0) bound = fminf(bound, pz - (g.loz + (float)(cz - r) * g.h));
+    if (cz + r < g.nz - 1) bound = fminf(bound, (g.loz + (float)(cz + r + 1) * g.h) - pz);
+    bound -= 1e-3f * g.h;
+    if (bound > 0.0f && bd[k - 1] <= bound * bound * 0.9999f) break;
+  }
+  for (int i = cnt; i < k; ++i) { bd[i] = 0.f; bj[i] = bj[0]; }  // fewer than k points in the cloud: pad with the nearest
+}
+
+// eigenvector of the smallest eigenvalue of a symmetric 3x3 (cyclic Jacobi, fp32)
+__device__ void smallest_eigenvector(const float* C, float* out) {
+  float a[9], v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int i = 0; i < 9; ++i) a[i] = C[i];
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    float off = 0.f;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        off = fmaxf(off, fabsf(a[3 * p + q]));
+        if (fabsf(a[3 * p + q]) <= 1e-37f) continue;
+        const float theta = (a[3 * q + q] - a[3 * p + p]) / (2.f * a[3 * p + q]);
+        const float t = (theta >= 0 ? 1.f : -1.f) / (fabsf(theta) + sqrtf(1.f + theta * theta));
+        const float c = 1.f / sqrtf(1.f + t * t), s = c * t;
+        for (int k = 0; k < 3; ++k) { const float akp = a[3 * k + p], akq = a[3 * k + q]; a[3 * k + p] = c * akp - s * akq; a[3 * k + q] = s * akp + c * akq; }
+        for (int k = 0; k < 3; ++k) { const float apk = a[3 * p + k], aqk = a[3 * q + k]; a[3 * p + k] = c * apk - s * aqk; a[3 * q + k] = s * apk + c * aqk; }
+        for (int k = 0; k < 3; ++k) { const float vkp = v[3 * k + p], vkq = v[3 * k + q]; v[3 * k + p] = c * vkp - s * vkq; v[3 * k + q] = s * vkp + c * vkq; }
+      }
+    if (off < 1e-12f * (fabsf(a[0]) + fabsf(a[4]) + fabsf(a[8]))) break;
+  }
+  int m = 0;
+  if (a[4] < a[0]) m = 1;
+  if (a[8] < a[4 * m]) m = 2;
+  out[0] = v[m]; out[1] = v[3 + m]; out[2] = v[6 + m];
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_normals(const NormalsDesc* __restrict__ descs, int k, float grid_cell, float vx, float vy, float vz) {
+  __shared__ double s_part[kWarps][16];
+  __shared__ float s_box[6];
+  __shared__ int s_scan[kWarps];
+  __shared__ Grid s_grid;
+  const NormalsDesc P = descs[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (P.n < 1) return;
+  {  // grid over the cloud (same construction as k_icp3d)
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int j = tid; j < P.n; j += kThreads)
+      for (int a = 0; a < 3; ++a) { const float v = P.pts[3 * j + a]; lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+    for (int a = 0; a < 3; ++a)
+      for (int o = 16; o > 0; o >>= 1) { lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o)); hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o)); }
+    float* s_f = reinterpret_cast<float*>(&s_part[0][0]);
+    if (lane == 0) for (int a = 0; a < 3; ++a) { s_f[warp * 6 + a] = lo[a]; s_f[warp * 6 + 3 + a] = hi[a]; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int a = 0; a < 3; ++a) {
+        float l = FLT_MAX, h = -FLT_MAX;
+        for (int w = 0; w < kWarps; ++w) { l = fminf(l, s_f[w * 6 + a]); h = fmaxf(h, s_f[w * 6 + 3 + a]); }
+        s_box[a] = l; s_box[3 + a] = h;
+      }
+      Grid g;
+      g.lox = s_box[0]; g.loy = s_box[1]; g.loz = s_box[2];
+      const float ex = s_box[3] - s_box[0], ey = s_box[4] - s_box[1], ez = s_box[5] - s_box[2];
+      float h = grid_cell > 0.f ? grid_cell : fmaxf(fmaxf(ex, fmaxf(ey, ez)) / 64.f, 1e-6f);
+      for (;;) {
+        g.nx = (int)floorf(ex / h) + 1; g.ny = (int)floorf(ey / h) + 1; g.nz = (int)floorf(ez / h) + 1;
+        if ((long long)g.nx * g.ny * g.nz <= kCellCap) break;
+        h *= 1.26f;
+      }
+      g.h = h; g.inv_h = 1.0f / h;
+      s_grid = g;
+    }
+    __syncthreads();
+  }
+  const Grid g = s_grid;
+  const int n_cells = g.nx * g.ny * g.nz;
+  for (int c = tid; c < n_cells; c += kThreads) P.cell_fill[c] = 0;
+  __syncthreads();
+  auto cell_of = [&](int j) {
+    return (cell_coord(P.pts[3 * j + 2], g.loz, g.inv_h, g.nz) * g.ny + cell_coord(P.pts[3 * j + 1], g.loy, g.inv_h, g.ny)) * g.nx +
+           cell_coord(P.pts[3 * j], g.lox, g.inv_h, g.nx);
+  };
+  for (int j = tid; j < P.n; j += kThreads) atomicAdd(P.cell_fill + cell_of(j), 1);
+  __syncthreads();
+  {
+    const int per = (n_cells + kThreads - 1) / kThreads;
+    const int c0 = tid * per, c1 = min(c0 + per, n_cells);
+    int local = 0;
+    for (int c = c0; c < c1; ++c) local += P.cell_fill[c];
+    int incl = local;
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int v = s_scan[lane];
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+      s_scan[lane] = v;
+    }
+    __syncthreads();
+    int run = incl - local + (warp > 0 ? s_scan[warp - 1] : 0);
+    for (int c = c0; c < c1; ++c) { const int q = P.cell_fill[c]; P.cell_start[c] = run; P.cell_fill[c] = 0; run += q; }
+    if (tid == 0) P.cell_start[n_cells] = P.n;
+  }
+  __syncthreads();
+  for (int j = tid; j < P.n; j += kThreads) {
+    const int c = cell_of(j);
+    const int pos = P.cell_start[c] + atomicAdd(P.cell_fill + c, 1);
+    P.sorted[pos] = make_float4(P.pts[3 * j], P.pts[3 * j + 1], P.pts[3 * j + 2], __int_as_float(j));
+  }
+  __syncthreads();
+
+  for (int i = tid; i < P.n; i += kThreads) {
+    const float px = P.pts[3 * i], py = P.pts[3 * i + 1], pz = P.pts[3 * i + 2];
+    float bd[kMaxK]; int bj[kMaxK];
+    knn_search(g, P.cell_start, P.sorted, px, py, pz, k, bd, bj);
+    float cen[3] = {0.f, 0.f, 0.f};
+    for (int q = 0; q < k; ++q) for (int a = 0; a < 3; ++a) cen[a] += P.pts[3 * bj[q] + a];   // :188-191
+    for (int a = 0; a < 3; ++a) cen[a] /= (float)k;
+    float C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int q = 0; q < k; ++q) {                                                              // :194-198
+      float d[3];
+      for (int a = 0; a < 3; ++a) d[a] = P.pts[3 * bj[q] + a] - cen[a];
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) C[3 * a + b] += d[a] * d[b];
+    }
+    float nv[3];
+    smallest_eigenvector(C, nv);                                                               // :201-202
+    const float ray = (px - vx) * nv[0] + (py - vy) * nv[1] + (pz - vz) * nv[2];              // :209-213
+    const float sgn = ray > 0.f ? -1.f : 1.f;
+    for (int a = 0; a < 3; ++a) P.normals[3 * i + a] = sgn * nv[a];
+  }
+}
+
 /* grow-only device/pinned arenas of the cloud engine, owned by the context */
 struct Icp3dState {
   void* d_arena = nullptr; size_t d_bytes = 0;
@@ -867,6 +1047,69 @@ extern "C" int32_t rst_solve_kabsch(rst_ctx* c, const rst_cloud* src, const rst_
   ICP_CUDA(cudaStreamSynchronize(stream));
   std::memcpy(pose_out, H + o_pose, 64);
   *ok_out = 1;
+#undef ICP_CUDA
+  return RST_OK;
+}
+
+/* ComputeNormals(cloud, tree, k, &normals) + OrientNormals(cloud, viewpoint, &normals)
+ * (point_cloud_utils.cpp:176-216) on the device. k (2..32) counts the point itself, as in the reference
+ * (rs_align_app.cpp:25 uses 16). normals_out: n x 3 floats, HOST memory. */
+extern "C" int32_t rst_cloud_normals(rst_ctx* c, const rst_cloud* cloud, int32_t k, const float* viewpoint, float grid_cell, float* normals_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  auto fail = [&](int code, const std::string& m) { rst::ctx_set_error(c, m); return code; };
+  if (!cloud || !viewpoint || !normals_out || cloud->n < 0 || (cloud->n > 0 && !cloud->xyz)) return fail(RST_ERR_INVALID_ARG, "null argument");
+  if (k < 2 || k > kMaxK) return fail(RST_ERR_INVALID_ARG, "k must be in [2, 32]");
+  if (cloud->n == 0) return RST_OK;
+#define ICP_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess) return fail(RST_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+  ICP_CUDA(cudaSetDevice(rst::ctx_device(c)));
+  cudaStream_t stream = rst::ctx_stream(c);
+  void (**free_fn)(void*) = nullptr;
+  void** slot = rst::ctx_ext_slot(c, &free_fn);
+  if (!*slot) { *slot = new Icp3dState(); *free_fn = icp3d_free; }
+  Icp3dState* st = static_cast<Icp3dState*>(*slot);
+  st->last_frames = 0;
+  const size_t n = (size_t)cloud->n;
+  size_t off = 0;
+  const size_t o_desc = off; off = align_up(off + sizeof(NormalsDesc));
+  const size_t o_pts = off; off = align_up(off + sizeof(float) * 3 * n);
+  const size_t upload = off;
+  const size_t o_nrm = off; off = align_up(off + sizeof(float) * 3 * n);
+  const size_t host_end = off;
+  const size_t o_cs = off; off = align_up(off + sizeof(int) * (kCellCap + 1));
+  const size_t o_cf = off; off = align_up(off + sizeof(int) * kCellCap);
+  const size_t o_sorted = off; off = align_up(off + sizeof(float4) * n);
+  const size_t total = off;
+  if (st->d_bytes < total) {
+    ICP_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(st->d_arena); st->d_arena = nullptr; st->d_bytes = 0;
+    ICP_CUDA(cudaMalloc(&st->d_arena, total));
+    st->d_bytes = total;
+  }
+  if (st->h_bytes < host_end) {
+    ICP_CUDA(cudaStreamSynchronize(stream));
+    cudaFreeHost(st->h_arena); st->h_arena = nullptr; st->h_bytes = 0;
+    ICP_CUDA(cudaMallocHost(&st->h_arena, host_end));
+    st->h_bytes = host_end;
+  }
+  char* H = static_cast<char*>(st->h_arena);
+  char* D = static_cast<char*>(st->d_arena);
+  NormalsDesc d;
+  d.pts = reinterpret_cast<const float*>(D + o_pts); d.n = cloud->n;
+  d.cell_start = reinterpret_cast<int*>(D + o_cs); d.cell_fill = reinterpret_cast<int*>(D + o_cf);
+  d.sorted = reinterpret_cast<float4*>(D + o_sorted); d.normals = reinterpret_cast<float*>(D + o_nrm);
+  std::memcpy(H + o_desc, &d, sizeof(d));
+  std::memcpy(H + o_pts, cloud->xyz, sizeof(float) * 3 * n);
+  ICP_CUDA(cudaMemcpyAsync(D, H, upload, cudaMemcpyHostToDevice, stream));
+  k_normals<<<1, kThreads, 0, stream>>>(reinterpret_cast<const NormalsDesc*>(D + o_desc), k, grid_cell, viewpoint[0], viewpoint[1], viewpoint[2]);
+  ICP_CUDA(cudaGetLastError());
+  rst::ctx_count_launches(c, 1);
+  ICP_CUDA(cudaMemcpyAsync(H + o_nrm, D + o_nrm, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, stream));
+  ICP_CUDA(cudaStreamSynchronize(stream));
+  std::memcpy(normals_out, H + o_nrm, sizeof(float) * 3 * n);
 #undef ICP_CUDA
   return RST_OK;
 }

@@ -139,3 +139,28 @@ def test_solve_kabsch_on_the_device(al):
     ok_k, T_k = al.solve_kabsch(src, dst, pairs)
     ok_i, T_i = al.icp3d_pairs([src], [dst], 16, T0=T_k)
     assert ok_i[0] and synth.pose_error(T_i[0], GOLD["T_big"]) < (1e-4, 1e-4)
+
+
+def test_cloud_normals_on_the_device(al):
+    """rst_cloud_normals vs the reference's own ComputeNormals + OrientNormals (compiled, oracle/_ref) when
+    present, and vs an analytic plane always (point_cloud_utils.cpp:176-216)."""
+    rng = np.random.default_rng(0)
+    xy = rng.uniform(-1, 1, size=(3000, 2))
+    n = np.array([0.3, -0.2, -1.0]); n /= np.linalg.norm(n)
+    z = (-2.0 - xy @ n[:2]) / n[2]
+    plane = np.column_stack([xy, z]).astype(np.float32)
+    got = al.cloud_normals(plane, k=16)
+    assert np.allclose(np.abs(got @ n), 1.0, atol=1e-3)
+    assert ((got * plane).sum(1) <= 0).all()                               # orientation rule, viewpoint = origin
+    assert np.allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-4)
+    flipped = al.cloud_normals(plane, k=16, viewpoint=(0.0, 0.0, 10.0))   # seen from behind: normals flip
+    assert ((flipped * (plane - np.float32([0, 0, 10]))).sum(1) <= 0).all() and np.allclose(flipped, -got, atol=1e-4)
+    # a depth-derived cloud (curved + planar parts) against the compiled reference
+    if O.ref_lib() is not None:
+        cloud = depth_clouds(1, 0)[0][:4000]
+        ref = O.ref_normals(cloud, k=16)
+        gpu = al.cloud_normals(cloud, k=16)
+        cosang = np.abs((ref * gpu).sum(1))
+        assert np.median(cosang) > 0.99999 and (cosang > 0.999).mean() > 0.97   # near-isotropic neighbourhoods may differ
+        assert ((gpu * cloud).sum(1) <= 1e-6).all()
+        assert ((ref * gpu).sum(1) > 0).mean() > 0.97                      # same orientation
