@@ -403,7 +403,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_val / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "seq640x480_f2f_3level_icp (BASELINE.json configs[1])", "width": W, "height": H,
+            "config": {"workload": f"seq{W}x{H}_f2f_3level_icp" + (" (BASELINE.json configs[1])" if (W, H) == (640, 480) else " (ad-hoc size)"), "width": W, "height": H,
                        "frames_per_gpu_per_step": FRAMES, "pairs_per_gpu_per_step": n_pairs, "levels": 3,
                        "iters_fine_to_coarse": list(ITERS), "accumulation": "fp32 per block (<=8192 px), fp64 across blocks and in the solve",
                        "l2_policy": f"inputs larger than L2: {FRAMES * npx * (2 + 16) * 1.3125 / 1e6:.0f} MB of depth pyramid + geometry maps streamed per step (L2 = 126 MB)",
@@ -435,7 +435,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--chunk", type=int, default=None, help="frames per upload/compute chunk of the e2e path")
+    ap.add_argument("--size", default=None, help="WxH override for ad-hoc runs (e.g. 1280x720); the default is the BASELINE metric's 640x480")
+    ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step override (default 129)")
     args = ap.parse_args()
+    global W, H, FRAMES, METRIC
+    if args.size:
+        W, H = (int(x) for x in args.size.lower().split("x"))
+        METRIC = f"icp_frame_pairs_per_sec_{W}x{H}"
+    if args.frames:
+        FRAMES = args.frames
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
