@@ -12,6 +12,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <unordered_map>
+#include <array>
 #include <vector>
 
 #include "rs_tracker/align/align_rgbd.hpp"
@@ -60,6 +62,35 @@ void PoseError(const Mat4d& est, const Mat4d& gt, double* t_err, double* r_err) 
 }
 }  // namespace
 
+// The replay app's voxel map (CloudAccumulator, rs_replay_app.cpp:76-129): the first point that lands in a
+// voxel stays; the voxel index TRUNCATES toward zero (`(p * 1/voxel).cast<int>()`, :109-111 — unlike
+// DownsampleVoxel, which floors).
+class CloudAccumulator {
+ public:
+  explicit CloudAccumulator(float voxel_size = 0.05f) : inv_(static_cast<float>(1.0 / voxel_size)) {}
+  void AddDepth(const Mat4d& xfm, const std::uint16_t* depth, int w, int h, const rs_tracker::Intrinsics& K, int step) {
+    for (int v = 0; v < h; v += step)
+      for (int u = 0; u < w; u += step) {
+        const std::uint16_t d = depth[v * w + u];
+        if (d == 0) continue;
+        const float z = d * 0.001f, x = (u - K.cx) * z / K.fx, y = (v - K.cy) * z / K.fy;
+        const float p[3] = {static_cast<float>(xfm.m[0] * x + xfm.m[4] * y + xfm.m[8] * z + xfm.m[12]),
+                            static_cast<float>(xfm.m[1] * x + xfm.m[5] * y + xfm.m[9] * z + xfm.m[13]),
+                            static_cast<float>(xfm.m[2] * x + xfm.m[6] * y + xfm.m[10] * z + xfm.m[14])};
+        const std::uint64_t key = Pack(static_cast<int>(p[0] * inv_), static_cast<int>(p[1] * inv_), static_cast<int>(p[2] * inv_));
+        map_.emplace(key, std::array<float, 3>{p[0], p[1], p[2]});   // emplace keeps the first point (:101-104)
+      }
+  }
+  std::size_t Size() const { return map_.size(); }
+
+ private:
+  static std::uint64_t Pack(int x, int y, int z) {
+    return (static_cast<std::uint64_t>(x & 0x1FFFFF) << 42) | (static_cast<std::uint64_t>(y & 0x1FFFFF) << 21) | static_cast<std::uint64_t>(z & 0x1FFFFF);
+  }
+  float inv_;
+  std::unordered_map<std::uint64_t, std::array<float, 3>> map_;
+};
+
 // minimal stand-in for the reference's Cloud3f accessors (cho::core::PointCloud<float,3>)
 struct VecCloud {
   std::vector<float> xyz;
@@ -104,6 +135,9 @@ int main(int argc, char** argv) {
   total.m[0] = total.m[5] = total.m[10] = total.m[15] = 1;
   const Mat4d T0 = CameraPose(0);
   rst_synth_render(&scene, T0.m, K.fx, K.fy, K.cx, K.cy, w, h, 0.001, nullptr, 0, prev.data(), w, nullptr);
+  CloudAccumulator acc(0.05f);
+  acc.AddDepth(total, prev.data(), w, h, K, 4);                      // acc.AddCloud(total_xfm, prev_cloud)  :240
+  const std::size_t map_first = acc.Size();
   int failures = 0;
   double t_err = 0, r_err = 0;
   for (int k = 1; k < n_frames; ++k) {
@@ -117,6 +151,7 @@ int main(int argc, char** argv) {
       Mat4d x{};
       for (int i = 0; i < 16; ++i) x.m[i] = xfm.m[i];
       total = Mul(total, x);                                         // total_xfm = total_xfm * xfm  :267
+      acc.AddDepth(total, curr.data(), w, h, K, 4);                  // acc.AddCloud(total_xfm, cloud) :268
       prev.swap(curr);                                               // prev_cloud = cloud           :270
     } else {
       std::printf("ALIGNMENT FAILED!! frame %d status %d (%s)\n", k, st.status, ctx.LastError());  // :272
@@ -127,5 +162,8 @@ int main(int argc, char** argv) {
   }
   std::printf("launches %lld, final drift %.4f m / %.4f rad over %d frames, failures %d\n",
               static_cast<long long>(rst_launch_count(ctx.get())), t_err, r_err, n_frames, failures);
-  return (failures == 0 && t_err < 0.02 && r_err < 0.02) ? 0 : 1;
+  // with correct poses consecutive frames re-observe the same surfaces: the map grows far slower than linearly
+  std::printf("voxel map: %zu voxels after the first frame, %zu after %d frames\n", map_first, acc.Size(), n_frames);
+  const bool map_ok = acc.Size() < map_first * 2 || n_frames > 40;
+  return (failures == 0 && t_err < 0.02 && r_err < 0.02 && map_ok) ? 0 : 1;
 }
