@@ -37,6 +37,7 @@ struct rst_ctx {
   int blocks_per_pair[RST_MAX_LEVELS]{}, chunks_per_row[RST_MAX_LEVELS]{}, n_chunks[RST_MAX_LEVELS]{};
   int groups[RST_MAX_LEVELS]{};
   uint32_t d_lo = 1, d_span = 0;
+  float range_scale = -1.f, range_zmin = 0.f, range_zmax = 0.f;  // parameters d_lo/d_span were derived from
 
   // HBM frame store (allocated once for max_w x max_h x max_frames)
   uint16_t* d_depth[RST_MAX_LEVELS]{};
@@ -311,8 +312,9 @@ int32_t rst_begin(rst_ctx* c, int32_t width, int32_t height, const rst_intrinsic
     const int cpb = kChunksPerBlock * c->groups[l];
     c->blocks_per_pair[l] = (c->n_chunks[l] + cpb - 1) / cpb;
   }
-  {
-    // integer form of the depth validity test: d != 0 && z_min <= float(d)*scale <= z_max (monotone in d)
+  if (!(c->range_scale == P.depth_scale && c->range_zmin == P.z_min && c->range_zmax == P.z_max)) {
+    // integer form of the depth validity test: d != 0 && z_min <= float(d)*scale <= z_max (monotone in d);
+    // the scan over all 65535 raw values is redone only when the three parameters change
     uint32_t lo = 65536u, hi = 0u;
     for (uint32_t d = 1; d <= 65535u; ++d) {
       const float z = (float)d * P.depth_scale;
@@ -320,6 +322,7 @@ int32_t rst_begin(rst_ctx* c, int32_t width, int32_t height, const rst_intrinsic
     }
     if (hi < lo) return fail(c, RST_ERR_INVALID_ARG, "no uint16 depth value falls inside [z_min, z_max]");
     c->d_lo = lo; c->d_span = hi - lo;
+    c->range_scale = P.depth_scale; c->range_zmin = P.z_min; c->range_zmax = P.z_max;
   }
   if (!same || c->store_dirty) {
     // row padding (columns >= w) must read as invalid depth
