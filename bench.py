@@ -219,7 +219,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     h_poses = np.tile(np.eye(4, dtype=np.float32).reshape(16), (n_pairs, 1))
     h_stats = (N.Stats * n_pairs)()
     K = N.Intrinsics(*intr)
-    fr = __import__("realsensetracker_b200.align", fromlist=["_frames"])._frames(frames)
+    from realsensetracker_b200.align import _frames
+    fr = _frames(frames)
     lib, ctx = al._lib, al._ctx
 
     def step_resident():

@@ -79,6 +79,82 @@ __device__ __forceinline__ int cell_coord(float p, float lo, float inv_h, int n)
   return c < 0 ? 0 : (c >= n ? n - 1 : c);
 }
 
+// Builds the uniform grid of a cloud inside one 1024-thread block: bounding box, cell size (grid_cell, or
+// extent/64; grown until the cell count fits kCellCap), counting sort of the points into cells
+// (cell_start[cells + 1], sorted[] = {x, y, z, original index}). All threads of the block must call it.
+__device__ Grid build_grid(const float* __restrict__ pts, int n, float grid_cell, int* cell_start, int* cell_fill, float4* sorted) {
+  __shared__ float s_lohi[kWarps][6];
+  __shared__ int s_scan[kWarps];
+  __shared__ Grid s_grid;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int j = tid; j < n; j += kThreads)
+    for (int a = 0; a < 3; ++a) { const float v = pts[3 * j + a]; lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+  for (int a = 0; a < 3; ++a)
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+  if (lane == 0) for (int a = 0; a < 3; ++a) { s_lohi[warp][a] = lo[a]; s_lohi[warp][3 + a] = hi[a]; }
+  __syncthreads();
+  if (tid == 0) {
+    float bl[3], bh[3];
+    for (int a = 0; a < 3; ++a) {
+      bl[a] = FLT_MAX; bh[a] = -FLT_MAX;
+      for (int w = 0; w < kWarps; ++w) { bl[a] = fminf(bl[a], s_lohi[w][a]); bh[a] = fmaxf(bh[a], s_lohi[w][3 + a]); }
+    }
+    Grid g;
+    g.lox = bl[0]; g.loy = bl[1]; g.loz = bl[2];
+    const float ex = bh[0] - bl[0], ey = bh[1] - bl[1], ez = bh[2] - bl[2];
+    float h = grid_cell > 0.f ? grid_cell : fmaxf(fmaxf(ex, fmaxf(ey, ez)) / 64.f, 1e-6f);
+    for (;;) {
+      g.nx = (int)floorf(ex / h) + 1; g.ny = (int)floorf(ey / h) + 1; g.nz = (int)floorf(ez / h) + 1;
+      if ((long long)g.nx * g.ny * g.nz <= kCellCap) break;
+      h *= 1.26f;
+    }
+    g.h = h; g.inv_h = 1.0f / h;
+    s_grid = g;
+  }
+  __syncthreads();
+  const Grid g = s_grid;
+  const int n_cells = g.nx * g.ny * g.nz;
+  auto cell_of = [&](int j) {
+    return (cell_coord(pts[3 * j + 2], g.loz, g.inv_h, g.nz) * g.ny + cell_coord(pts[3 * j + 1], g.loy, g.inv_h, g.ny)) * g.nx +
+           cell_coord(pts[3 * j], g.lox, g.inv_h, g.nx);
+  };
+  for (int c = tid; c < n_cells; c += kThreads) cell_fill[c] = 0;
+  __syncthreads();
+  for (int j = tid; j < n; j += kThreads) atomicAdd(cell_fill + cell_of(j), 1);
+  __syncthreads();
+  {
+    const int per = (n_cells + kThreads - 1) / kThreads;
+    const int c0 = tid * per, c1 = min(c0 + per, n_cells);
+    int local = 0;
+    for (int c = c0; c < c1; ++c) local += cell_fill[c];
+    int incl = local;  // inclusive scan of the per-thread totals
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int v = s_scan[lane];
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+      s_scan[lane] = v;
+    }
+    __syncthreads();
+    int run = incl - local + (warp > 0 ? s_scan[warp - 1] : 0);
+    for (int c = c0; c < c1; ++c) { const int k = cell_fill[c]; cell_start[c] = run; cell_fill[c] = 0; run += k; }
+    if (tid == 0) cell_start[n_cells] = n;
+  }
+  __syncthreads();
+  for (int j = tid; j < n; j += kThreads) {
+    const int c = cell_of(j);
+    const int pos = cell_start[c] + atomicAdd(cell_fill + c, 1);
+    sorted[pos] = make_float4(pts[3 * j], pts[3 * j + 1], pts[3 * j + 2], __int_as_float(j));
+  }
+  __syncthreads();
+  return g;
+}
+
 // exact nearest neighbour of p in the gridded dst cloud; ties go to the lowest original index
 __device__ void nn_search(const Grid& g, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
                           float px, float py, float pz, int* best_j, float* best_d2) {
@@ -240,91 +316,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
   __shared__ double s_part[kWarps][16];
   __shared__ double s_sum[16];
   __shared__ float s_T[16];
-  __shared__ float s_box[6];
-  __shared__ int s_scan[kWarps];
-  __shared__ Grid s_grid;
 
   PairDesc P = descs[blockIdx.x];
   if (P.n_ptr) P.n = *P.n_ptr;
   if (P.m_ptr) P.m = *P.m_ptr;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   if (P.n < 3 || P.m < 3) {  // align_icp.cpp:77-79: false, pose untouched
     if (tid == 0 && P.res) { rst_icp3d_result r{}; *P.res = r; }
     return;
   }
 
-  // ---- uniform grid over dst: bounding box
-  {
-    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (int j = tid; j < P.m; j += kThreads)
-      for (int a = 0; a < 3; ++a) { const float v = P.dst[3 * j + a]; lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
-    for (int a = 0; a < 3; ++a)
-      for (int o = 16; o > 0; o >>= 1) {
-        lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
-        hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
-      }
-    float* s_f = reinterpret_cast<float*>(&s_part[0][0]);  // [warp][6]
-    if (lane == 0) for (int a = 0; a < 3; ++a) { s_f[warp * 6 + a] = lo[a]; s_f[warp * 6 + 3 + a] = hi[a]; }
-    __syncthreads();
-    if (tid == 0) {
-      for (int a = 0; a < 3; ++a) {
-        float l = FLT_MAX, h = -FLT_MAX;
-        for (int w = 0; w < kWarps; ++w) { l = fminf(l, s_f[w * 6 + a]); h = fmaxf(h, s_f[w * 6 + 3 + a]); }
-        s_box[a] = l; s_box[3 + a] = h;
-      }
-      Grid g;
-      g.lox = s_box[0]; g.loy = s_box[1]; g.loz = s_box[2];
-      const float ex = s_box[3] - s_box[0], ey = s_box[4] - s_box[1], ez = s_box[5] - s_box[2];
-      float h = grid_cell > 0.f ? grid_cell : fmaxf(fmaxf(ex, fmaxf(ey, ez)) / 64.f, 1e-6f);
-      for (;;) {
-        g.nx = (int)floorf(ex / h) + 1; g.ny = (int)floorf(ey / h) + 1; g.nz = (int)floorf(ez / h) + 1;
-        if ((long long)g.nx * g.ny * g.nz <= kCellCap) break;
-        h *= 1.26f;
-      }
-      g.h = h; g.inv_h = 1.0f / h;
-      s_grid = g;
-    }
-    __syncthreads();
-  }
-  const Grid g = s_grid;
-  const int n_cells = g.nx * g.ny * g.nz;
-
-  // ---- counting sort of dst into cells
-  for (int c = tid; c < n_cells; c += kThreads) P.cell_fill[c] = 0;
-  __syncthreads();
-  for (int j = tid; j < P.m; j += kThreads) {
-    const int c = (cell_coord(P.dst[3 * j + 2], g.loz, g.inv_h, g.nz) * g.ny + cell_coord(P.dst[3 * j + 1], g.loy, g.inv_h, g.ny)) * g.nx +
-                  cell_coord(P.dst[3 * j], g.lox, g.inv_h, g.nx);
-    atomicAdd(P.cell_fill + c, 1);
-  }
-  __syncthreads();
-  {
-    const int per = (n_cells + kThreads - 1) / kThreads;
-    const int c0 = tid * per, c1 = min(c0 + per, n_cells);
-    int local = 0;
-    for (int c = c0; c < c1; ++c) local += P.cell_fill[c];
-    int incl = local;  // inclusive scan of the per-thread totals
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-    if (lane == 31) s_scan[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      int v = s_scan[lane];
-      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-      s_scan[lane] = v;
-    }
-    __syncthreads();
-    int run = incl - local + (warp > 0 ? s_scan[warp - 1] : 0);
-    for (int c = c0; c < c1; ++c) { const int k = P.cell_fill[c]; P.cell_start[c] = run; P.cell_fill[c] = 0; run += k; }
-    if (tid == 0) P.cell_start[n_cells] = P.m;
-  }
-  __syncthreads();
-  for (int j = tid; j < P.m; j += kThreads) {
-    const float x = P.dst[3 * j], y = P.dst[3 * j + 1], z = P.dst[3 * j + 2];
-    const int c = (cell_coord(z, g.loz, g.inv_h, g.nz) * g.ny + cell_coord(y, g.loy, g.inv_h, g.ny)) * g.nx + cell_coord(x, g.lox, g.inv_h, g.nx);
-    const int pos = P.cell_start[c] + atomicAdd(P.cell_fill + c, 1);
-    P.sorted[pos] = make_float4(x, y, z, __int_as_float(j));
-  }
-  __syncthreads();
+  // ---- uniform grid over dst
+  const Grid g = build_grid(P.dst, P.m, grid_cell, P.cell_start, P.cell_fill, P.sorted);
 
   // ---- src centroid (ComputeCentroid, point_cloud_utils.cpp:92-98), pose -> shared
   float smean[3];
@@ -638,78 +641,10 @@ __device__ void smallest_eigenvector(const float* C, float* out) {
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_normals(const NormalsDesc* __restrict__ descs, int k, float grid_cell, float vx, float vy, float vz) {
-  __shared__ double s_part[kWarps][16];
-  __shared__ float s_box[6];
-  __shared__ int s_scan[kWarps];
-  __shared__ Grid s_grid;
   const NormalsDesc P = descs[blockIdx.x];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   if (P.n < 1) return;
-  {  // grid over the cloud (same construction as k_icp3d)
-    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (int j = tid; j < P.n; j += kThreads)
-      for (int a = 0; a < 3; ++a) { const float v = P.pts[3 * j + a]; lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
-    for (int a = 0; a < 3; ++a)
-      for (int o = 16; o > 0; o >>= 1) { lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o)); hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o)); }
-    float* s_f = reinterpret_cast<float*>(&s_part[0][0]);
-    if (lane == 0) for (int a = 0; a < 3; ++a) { s_f[warp * 6 + a] = lo[a]; s_f[warp * 6 + 3 + a] = hi[a]; }
-    __syncthreads();
-    if (tid == 0) {
-      for (int a = 0; a < 3; ++a) {
-        float l = FLT_MAX, h = -FLT_MAX;
-        for (int w = 0; w < kWarps; ++w) { l = fminf(l, s_f[w * 6 + a]); h = fmaxf(h, s_f[w * 6 + 3 + a]); }
-        s_box[a] = l; s_box[3 + a] = h;
-      }
-      Grid g;
-      g.lox = s_box[0]; g.loy = s_box[1]; g.loz = s_box[2];
-      const float ex = s_box[3] - s_box[0], ey = s_box[4] - s_box[1], ez = s_box[5] - s_box[2];
-      float h = grid_cell > 0.f ? grid_cell : fmaxf(fmaxf(ex, fmaxf(ey, ez)) / 64.f, 1e-6f);
-      for (;;) {
-        g.nx = (int)floorf(ex / h) + 1; g.ny = (int)floorf(ey / h) + 1; g.nz = (int)floorf(ez / h) + 1;
-        if ((long long)g.nx * g.ny * g.nz <= kCellCap) break;
-        h *= 1.26f;
-      }
-      g.h = h; g.inv_h = 1.0f / h;
-      s_grid = g;
-    }
-    __syncthreads();
-  }
-  const Grid g = s_grid;
-  const int n_cells = g.nx * g.ny * g.nz;
-  for (int c = tid; c < n_cells; c += kThreads) P.cell_fill[c] = 0;
-  __syncthreads();
-  auto cell_of = [&](int j) {
-    return (cell_coord(P.pts[3 * j + 2], g.loz, g.inv_h, g.nz) * g.ny + cell_coord(P.pts[3 * j + 1], g.loy, g.inv_h, g.ny)) * g.nx +
-           cell_coord(P.pts[3 * j], g.lox, g.inv_h, g.nx);
-  };
-  for (int j = tid; j < P.n; j += kThreads) atomicAdd(P.cell_fill + cell_of(j), 1);
-  __syncthreads();
-  {
-    const int per = (n_cells + kThreads - 1) / kThreads;
-    const int c0 = tid * per, c1 = min(c0 + per, n_cells);
-    int local = 0;
-    for (int c = c0; c < c1; ++c) local += P.cell_fill[c];
-    int incl = local;
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-    if (lane == 31) s_scan[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      int v = s_scan[lane];
-      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-      s_scan[lane] = v;
-    }
-    __syncthreads();
-    int run = incl - local + (warp > 0 ? s_scan[warp - 1] : 0);
-    for (int c = c0; c < c1; ++c) { const int q = P.cell_fill[c]; P.cell_start[c] = run; P.cell_fill[c] = 0; run += q; }
-    if (tid == 0) P.cell_start[n_cells] = P.n;
-  }
-  __syncthreads();
-  for (int j = tid; j < P.n; j += kThreads) {
-    const int c = cell_of(j);
-    const int pos = P.cell_start[c] + atomicAdd(P.cell_fill + c, 1);
-    P.sorted[pos] = make_float4(P.pts[3 * j], P.pts[3 * j + 1], P.pts[3 * j + 2], __int_as_float(j));
-  }
-  __syncthreads();
+  const Grid g = build_grid(P.pts, P.n, grid_cell, P.cell_start, P.cell_fill, P.sorted);
 
   for (int i = tid; i < P.n; i += kThreads) {
     const float px = P.pts[3 * i], py = P.pts[3 * i + 1], pz = P.pts[3 * i + 2];
