@@ -179,7 +179,7 @@ def run_reference(args, rank: int, world: int):
         "gpu_launches": 0,
         "pose_err_vs_gt": {"t_m_max": max(e[0] for e in errs), "r_rad_max": max(e[1] for e in errs)},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 # --------------------------------------------------------------------------------------------
@@ -420,7 +420,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             "pose_err_vs_gt": {"t_m_max": float(errs[:, 0].max()), "r_rad_max": float(errs[:, 1].max()),
                                "pairs_failed": status_bad},
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
     al.close()
     al_b.close()
     if world > 1:
@@ -428,7 +428,15 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         dist.destroy_process_group()
 
 
+RESULT_OUT = sys.stdout
+
+
 def main():
+    # stdout carries exactly ONE JSON line: everything libraries print (NCCL's version banner, warnings)
+    # is sent to stderr by pointing fd 1 at fd 2 and keeping a private handle on the real stdout
+    global RESULT_OUT
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
