@@ -115,7 +115,10 @@ typedef struct rst_params {
   float photo_weight;             /* lambda of the photometric term (needs rst_frame.rgb), 0 = off:
                                      cost = sum r_geo^2 + lambda * sum (I_dst(pi(p')) - I_src)^2  */
   int32_t tiling;                 /* RST_TILING_*: how pixels are cut into blocks */
-  int32_t reserved[3];
+  float converge_eps;             /* > 0: a pair skips the remaining iterations of a level once an update
+                                     has |omega| < eps (rad) and |v| < eps (m); 0 (default) = fixed count,
+                                     like the reference's AlignIcp3d (no convergence test, align_icp.cpp:92) */
+  int32_t reserved[2];
 } rst_params;
 
 /* Per-pair result statistics. A/b/sum_wr2/count belong to the LAST evaluated

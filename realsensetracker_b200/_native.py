@@ -41,7 +41,7 @@ class Params(C.Structure):
                 ("dist_max", C.c_float), ("normal_cos_min", C.c_float), ("normal_depth_tol", C.c_float),
                 ("pyr_depth_tol", C.c_int32), ("robust_kind", C.c_int32), ("robust_scale", C.c_float),
                 ("min_count", C.c_int32), ("damping", C.c_float), ("photo_weight", C.c_float),
-                ("tiling", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("tiling", C.c_int32), ("converge_eps", C.c_float), ("reserved", C.c_int32 * 2)]
 
 
 class Stats(C.Structure):

@@ -62,6 +62,7 @@ struct rst_ctx {
   float* d_poses_cm = nullptr;
   rst_stats* d_stats = nullptr;
   uint32_t* d_tickets = nullptr;
+  uint8_t* d_done = nullptr;            // per pair: converged on the current level (converge_eps > 0)
   float* d_partials = nullptr;
   int max_blocks = 0;
   int32_t* d_idx = nullptr;
@@ -186,7 +187,7 @@ void rst_ctx_destroy(rst_ctx* c) {
   if (c->ext && c->ext_free) c->ext_free(c->ext);
   for (int l = 0; l < RST_MAX_LEVELS; ++l) { cudaFree(c->d_depth[l]); cudaFree(c->d_geom[l]); }
   cudaFree(c->d_pairs); cudaFree(c->d_poses_in); cudaFree(c->d_master); cudaFree(c->d_pose_f32);
-  cudaFree(c->d_poses_cm); cudaFree(c->d_stats); cudaFree(c->d_tickets); cudaFree(c->d_partials);
+  cudaFree(c->d_poses_cm); cudaFree(c->d_stats); cudaFree(c->d_tickets); cudaFree(c->d_partials); cudaFree(c->d_done);
   cudaFree(c->d_idx);
   cudaFree(c->d_rgb);
   for (int l = 0; l < RST_MAX_LEVELS; ++l) cudaFree(c->d_int[l]);
@@ -264,6 +265,8 @@ int32_t rst_ctx_create(int32_t device, int32_t max_w, int32_t max_h, int32_t max
   CREATE_TRY(cudaMalloc(&c->d_stats, sizeof(rst_stats) * np));
   CREATE_TRY(cudaMalloc(&c->d_tickets, sizeof(uint32_t) * np));
   CREATE_TRY(cudaMemset(c->d_tickets, 0, sizeof(uint32_t) * np));
+  CREATE_TRY(cudaMalloc(&c->d_done, np));
+  CREATE_TRY(cudaMemset(c->d_done, 0, np));
   CREATE_TRY(cudaMalloc(&c->d_partials, sizeof(float) * kAccPad * (size_t)c->max_blocks * np));
   CREATE_TRY(cudaMallocHost(&c->h_pairs, sizeof(int2) * np));
   CREATE_TRY(cudaMallocHost(&c->h_poses, sizeof(float) * 16 * np));
@@ -288,6 +291,7 @@ int32_t rst_begin(rst_ctx* c, int32_t width, int32_t height, const rst_intrinsic
     return fail(c, RST_ERR_INVALID_ARG, "depth_scale, dist_max, z range and focal lengths must be positive");
   if (P.robust_kind < 0 || P.robust_kind > 2) return fail(c, RST_ERR_INVALID_ARG, "unknown robust_kind");
   if (P.tiling < 0 || P.tiling > 1) return fail(c, RST_ERR_INVALID_ARG, "unknown tiling");
+  if (!(P.converge_eps >= 0.f)) return fail(c, RST_ERR_INVALID_ARG, "converge_eps must be >= 0");
   if (P.robust_kind != RST_ROBUST_NONE && !(P.robust_scale > 0.f)) return fail(c, RST_ERR_INVALID_ARG, "robust_scale must be positive");
   if ((width >> (P.num_levels - 1)) < 8 || (height >> (P.num_levels - 1)) < 8)
     return fail(c, RST_ERR_INVALID_ARG, "coarsest pyramid level smaller than 8x8");
@@ -492,6 +496,8 @@ static void fill_icp_args(const rst_ctx* c, int l, IcpArgs* a) {
   a->min_count = c->P.min_count;
   a->damping = c->P.damping;
   a->update_pose = 1;
+  a->converge_eps = c->P.converge_eps;
+  a->done = c->P.converge_eps > 0.f ? c->d_done : nullptr;
   a->idx_out = nullptr;
 }
 
@@ -539,6 +545,7 @@ static int32_t pairs_iterate(rst_ctx* c, int first, int n) {
   for (int l = c->num_levels - 1; l >= 0; --l) {
     IcpArgs a{};
     fill_icp_args(c, l, &a);
+    if (a.done) RST_CUDA(c, cudaMemsetAsync(c->d_done + first, 0, (size_t)n, c->stream));  // every level starts active
     const int ph = prof_begin(c, 1, l);
     int nl = 0;
     for (int it = 0; it < c->P.iters[l]; ++it) {
@@ -877,6 +884,7 @@ int32_t rst_evaluate(rst_ctx* c, int32_t src_slot, int32_t dst_slot, int32_t lev
   fill_icp_args(c, level, &a);
   a.pair_offset = sp;
   a.update_pose = 0;
+  a.done = nullptr;
   a.idx_out = idx_out ? c->d_idx : nullptr;
   RST_CUDA(c, launch_icp_iter(a, 1, c->P.robust_kind, c->P.normal_cos_min > -1.0f, idx_out != nullptr, c->photo, c->stream));
   c->launches += 1;

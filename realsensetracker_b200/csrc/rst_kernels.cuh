@@ -101,6 +101,8 @@ struct IcpArgs {
   rst_stats* stats;
   int32_t min_count;
   float damping;
+  float converge_eps;         // > 0: set done[pair] when an update is smaller than this
+  uint8_t* done;              // [pair]: skip the rest of the level (nullptr when converge_eps == 0)
   int32_t update_pose;        // 0: evaluate only
   int32_t* idx_out;           // WRITE_IDX: [pair-local][h*w]
 };

@@ -332,3 +332,26 @@ def test_abi_edge_cases_on_the_device(seq_small):
         assert al.launch_count > 0
     finally:
         al.close()
+
+
+def test_convergence_early_exit_matches_oracle(seq640):
+    """converge_eps > 0: a pair leaves a level once an update is below the threshold (the reference has no
+    such test, align_icp.cpp:92 — fixed count stays the default)."""
+    frames, gt, intr = seq640
+    kw = dict(converge_eps=2e-5)
+    P, Po = both_params(**kw)
+    al = Aligner(640, 480, 8, 4)
+    try:
+        T, st = al.align_pairs(frames[1:4], frames[0:3], intr, P)
+        Tfull, stfull = al.align_pairs(frames[1:4], frames[0:3], intr, default_params())
+        for i in range(3):
+            To, so = O.align_pair(frames[i + 1], frames[i], intr, Po)
+            assert st[i].status == 0
+            assert st[i].iterations < 19 and abs(st[i].iterations - so.iterations) <= 1, (st[i].iterations, so.iterations)
+            dt, dr = synth.pose_error(T[i], To)
+            assert dt < 1e-4 and dr < 1e-4
+            ft, fr = synth.pose_error(T[i], Tfull[i])               # stopping early costs (almost) nothing
+            assert ft < 1e-4 and fr < 1e-4
+            assert stfull[i].iterations == 19
+    finally:
+        al.close()

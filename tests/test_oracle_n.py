@@ -162,3 +162,13 @@ def test_initial_pose_convention_and_failure():
     zero = np.zeros_like(f[0])
     T, st = O.align_pair(zero, f[0], intr, P)
     assert st.status == 1 and np.array_equal(T, np.eye(4)) and st.count == 0
+
+
+def test_convergence_early_exit_in_the_oracle():
+    intr = tuple(GOLD["intr"])
+    f = GOLD["frames"]
+    T_full, s_full = O.align_pair(f[1], f[0], intr, O.default_params())
+    T_early, s_early = O.align_pair(f[1], f[0], intr, O.default_params(converge_eps=5e-5))
+    assert s_full.iterations == 19 and 3 <= s_early.iterations < 19
+    dt, dr = synth.pose_error(T_early, T_full)
+    assert dt < 2e-4 and dr < 2e-4
