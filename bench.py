@@ -348,6 +348,15 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
     e2e_value = total_pairs / (ms_e2e * 1e-3)
+
+    # the plain blocking call (one context, nothing overlapped), for reference beside the streaming form
+    def step_blocking():
+        h_poses[:] = np.eye(4, dtype=np.float32).reshape(16)   # poses are in/out: every step starts from the identity prior
+        rc = lib.rst_align_sequence(ctx, fr, FRAMES, C.byref(K), C.byref(P), h_poses.ctypes.data, C.addressof(h_stats))
+        if rc != 0:
+            raise RuntimeError(lib.rst_last_error(ctx).decode())
+    ms_blk, _, _, _ = timed(step_blocking, max(5, args.steps // 2), 2)
+    blocking_value = world * n_pairs * max(5, args.steps // 2) / (ms_blk * 1e-3)
     Te2e = cm_to_pose(h_poses)
     assert np.array_equal(Te2e, Tres), "host-path and device-resident results differ"
     status_bad = sum(1 for s in h_stats if s.status != 0)
@@ -428,7 +437,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": ms_e2e / args.steps, "gpu_launches": int(launches_e2e),
-                    "api": "rst_align_sequence_async + rst_wait, two contexts per GPU alternating (copy of step k+1 under the kernels of step k)"},
+                    "api": "rst_align_sequence_async + rst_wait, two contexts per GPU alternating (copy of step k+1 under the kernels of step k)",
+                    "blocking_call": {"value": blocking_value, "unit": "pairs/s", "api": "rst_align_sequence (one context, H2D then kernels then D2H)"}},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
