@@ -81,6 +81,28 @@ def ncu_traffic():
     return None
 
 
+def bind_to_gpu_numa(props) -> str:
+    """Best effort: run this rank on the cores of the NUMA node its GPU hangs off, so that the pinned
+    frame buffers (first touch) and the H2D copies stay on the local socket. With 8 ranks the host memory
+    system, not PCIe, limits the end-to-end figure otherwise."""
+    try:
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"numa node {node}: no allowed cpu"
+        os.sched_setaffinity(0, cpus)
+        return f"numa node {node}, {len(cpus)} cpus"
+    except Exception as e:  # not fatal: the bench still runs, only possibly across sockets
+        return f"not bound ({type(e).__name__})"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -199,6 +221,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         raise SystemExit("bench.py: no CUDA device — the alignment path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa(torch.cuda.get_device_properties(local_rank)) if world > 1 else "single rank: not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -433,7 +456,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                        "frames_per_gpu_per_step": FRAMES, "pairs_per_gpu_per_step": n_pairs, "levels": 3,
                        "iters_fine_to_coarse": list(ITERS), "accumulation": "fp32 per block (<=8192 px), fp64 across blocks and in the solve",
                        "l2_policy": f"inputs larger than L2: {FRAMES * npx * (2 + 16) * 1.3125 / 1e6:.0f} MB of depth pyramid + geometry maps streamed per step (L2 = 126 MB)",
-                       "parallelism": f"pairs sharded, {world} rank(s), NCCL all_gather of poses only"},
+                       "parallelism": f"pairs sharded, {world} rank(s), NCCL all_gather of poses only", "host_binding_rank0": numa},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": ms_e2e / args.steps, "gpu_launches": int(launches_e2e),
