@@ -28,3 +28,17 @@ def test_replay_loop_through_the_cpp_api():
     res = subprocess.run([str(exe), "12"], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "failures 0" in res.stdout
+
+
+def test_eigen_overload_compiles_against_the_stand_in_eigen(tmp_path):
+    """The Isometry3f / Matrix3f overload of AlignRgbd is only compiled when <Eigen/Geometry> exists; real
+    Eigen is absent here, so the syntax is checked against the stand-in headers of oracle/shim (compile only)."""
+    src = tmp_path / "eig.cpp"
+    src.write_text('#include "rs_tracker/align/align_rgbd.hpp"\n'
+                   '#ifndef RS_TRACKER_HAVE_EIGEN\n#error "Eigen overload not enabled"\n#endif\n'
+                   'bool f(rs_tracker::AlignContext& c, const rs_tracker::DepthFrame& a, const rs_tracker::DepthFrame& b) {\n'
+                   '  Eigen::Matrix3f K = Eigen::Matrix3f::Identity(); Eigen::Isometry3f T = Eigen::Isometry3f::Identity();\n'
+                   '  rs_tracker::AlignParams p; return rs_tracker::AlignRgbd(c, a, b, K, p, &T); }\n')
+    res = subprocess.run(["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-I", str(ROOT / "include"), "-I", str(ROOT / "oracle" / "shim"), str(src)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
