@@ -239,6 +239,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     al = Aligner(W, H, FRAMES, n_pairs, device=local_rank, stream=stream.cuda_stream)
     if args.chunk is not None:
         al.set_pipeline_chunk(args.chunk)
+    if args.no_split:
+        al.set_stream_split(0)
     src_slots = np.arange(1, FRAMES, dtype=np.int32)
     dst_slots = np.arange(0, FRAMES - 1, dtype=np.int32)
     d_poses = torch.empty((n_pairs, 16), dtype=torch.float32, device=dev)
@@ -334,8 +336,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     early_err = np.array([synth.pose_error(early_poses[i], gt[i]) for i in range(n_pairs)])
     P = P_fixed
 
-    # ---- roofline region: the same steps on ONE stream (stream split off) so that CUDA events around
-    #      each level's launches time the kernels in isolation, not two overlapping halves
+    # ---- roofline region: the same steps with CUDA events around every kernel group (the fused launch; one
+    #      pre-processing launch per level), all on ONE stream so that each is timed in isolation
     al.set_stream_split(0)
     with torch.cuda.stream(stream):
         for _ in range(2):
@@ -344,7 +346,28 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     ms_single, _, _, _ = timed(step_resident, args.steps, 0)
     prof = al.profile_read()
     al.profile_enable(False)
-    al.set_stream_split(32)
+
+    # ---- the other two schedules, for comparison (rst_set_schedule): fully fused (ONE cluster launch for all 19
+    #      iterations of a batch) and hybrid (coarse levels fused, finest level one launch per iteration)
+    def schedule_region(sched):
+        al.set_schedule(sched)
+        al.set_stream_split(0)
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                step_resident()
+        al.profile_enable(True)
+        ms_1s, _, _, _ = timed(step_resident, args.steps, 0)
+        pr = al.profile_read()
+        al.profile_enable(False)
+        al.set_stream_split(0 if args.no_split else 32)
+        ms_sp, _, _, _ = timed(step_resident, args.steps, 0)
+        return ms_1s, ms_sp, pr
+    ms_fused_1s, ms_fused, prof_fused = schedule_region(1)
+    ms_hybrid_1s, ms_hybrid, prof_hy = schedule_region(3)
+    al.set_schedule(0)
+    with torch.cuda.stream(stream):
+        step_resident()     # d_poses holds the default schedule's result again
+    torch.cuda.synchronize()
 
     # correctness of what was timed: poses vs ground truth, and (N>1) the gathered block of this rank
     poses_dev = d_poses.cpu().numpy()
@@ -388,31 +411,48 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     if rank == 0:
         peak, peak_src = measured_peak()
         npx = W * H
-        n_l0 = prof.launches_icp[0]
-        t_l0 = prof.ms_icp[0] * 1e-3 / max(n_l0, 1)                    # average level-0 launch, seconds
-        bytes_layout = n_pairs * (2.0 * npx + 16.0 * mean_count)       # this layout's compulsory bytes per launch
-        bytes_survey = n_pairs * float(SURVEY_BYTES_PER_PX) * npx      # SURVEY.md §8(d) figure per launch
+        assoc_frac = mean_count / npx                                  # associated fraction of the finest level (last iterate)
+        # compulsory bytes of this layout per pair-iteration on level l: 2 B x pixels + 16 B x associated pixels
+        lvl_px = [(W >> l) * (H >> l) for l in range(3)]
+        bytes_pair_iter = [2.0 * p + 16.0 * assoc_frac * p for p in lvl_px]
+        n_l0 = max(prof.launches_icp[0], 1)
+        t_l0 = prof.ms_icp[0] * 1e-3 / n_l0                            # average level-0 launch, seconds
+        bytes_layout = n_pairs * bytes_pair_iter[0]                    # per level-0 launch
+        bytes_survey = n_pairs * float(SURVEY_BYTES_PER_PX) * npx
         ach = bytes_layout / t_l0 / 1e9
         ach_s = bytes_survey / t_l0 / 1e9
+        t_coarse = prof_hy.ms_icp_fused * 1e-3 / max(prof_hy.launches_icp_fused, 1)
+        bytes_coarse = n_pairs * sum(ITERS[l] * bytes_pair_iter[l] for l in (1, 2))
+        lvl_us = [prof.ms_icp[l] * 1e3 / max(prof.launches_icp[l], 1) for l in range(3)]
+        t_ff = prof_fused.ms_icp_fused * 1e-3 / max(prof_fused.launches_icp_fused, 1)
+        bytes_all = n_pairs * sum(ITERS[l] * bytes_pair_iter[l] for l in range(3))
         tr = ncu_traffic()
-        icp_ms = sum(prof.ms_icp[l] for l in range(3))
         pre_ms = sum(prof.ms_preprocess[l] for l in range(3))
-        ms_val_split, ms_val = ms_val, ms_single   # stage shares refer to the single-stream roofline region
         roofline = {
-            "kernel": "k_icp_iter<level 0> (fused association + point-to-plane J^T J / J^T r + reduction + solve)",
+            "kernel": "k_icp_iter<level 0> (fused association + point-to-plane J^T J / J^T r + reduction + solve), %d launches per step" % ITERS[0],
             "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "traffic": (tr or {}).get("dram_bytes_per_launch"),
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": bytes_layout,
             "bytes_per_px": {"src_depth": 2, "dst_geometry_gather": 16, "associated_px_per_pair": mean_count},
-            "avg_launch_us": t_l0 * 1e6, "launches_timed": n_l0,
+            "avg_launch_us": t_l0 * 1e6, "launches_timed": prof.launches_icp[0],
             "survey_equiv": {"bytes_per_px": SURVEY_BYTES_PER_PX, "achieved": ach_s, "frac": ach_s / peak},
-            "stage_share_of_step": {"icp_l0": prof.ms_icp[0] / ms_val, "icp_l1": prof.ms_icp[1] / ms_val,
-                                    "icp_l2": prof.ms_icp[2] / ms_val, "preprocess": pre_ms / ms_val,
-                                    "other": max(0.0, 1.0 - (icp_ms + pre_ms) / ms_val)},
-            "measured_in": "single-stream region of the same steps (ms_per_step %.3f); the headline value uses the two-stream split" % (ms_single / args.steps),
+            "level_launch_us": lvl_us,
+            "level_frac": [n_pairs * bytes_pair_iter[l] / (lvl_us[l] * 1e-6) / 1e9 / peak if lvl_us[l] > 0 else None for l in range(3)],
+            "stage_share_of_step": {"icp_l0": prof.ms_icp[0] / ms_single, "icp_l1": prof.ms_icp[1] / ms_single,
+                                    "icp_l2": prof.ms_icp[2] / ms_single, "preprocess": pre_ms / ms_single,
+                                    "other": max(0.0, 1.0 - (sum(prof.ms_icp[l] for l in range(3)) + pre_ms) / ms_single)},
+            "schedules": {
+                "auto": {"what": "default = one launch per iteration per level (k_icp_iter), two-stream split for large batches", "value": value},
+                "fused": {"what": "rst_set_schedule(1): k_icp_fused, one cluster of CTAs per pair, all %d iterations of all levels in ONE launch "
+                                  "(DSMEM reduction, no global partials)" % sum(ITERS),
+                          "value": total_pairs / (ms_fused * 1e-3), "launch_us": t_ff * 1e6, "achieved": bytes_all / t_ff / 1e9,
+                          "frac": bytes_all / t_ff / 1e9 / peak},
+                "hybrid": {"what": "rst_set_schedule(3): levels 2 and 1 (%d + %d iterations) fused in one launch, level 0 one launch per iteration" % (ITERS[2], ITERS[1]),
+                           "value": total_pairs / (ms_hybrid * 1e-3), "coarse_launch_us": t_coarse * 1e6,
+                           "coarse_frac": bytes_coarse / t_coarse / 1e9 / peak if t_coarse > 0 else None}},
+            "measured_in": "a second timed region of the same steps on one stream with CUDA events around every kernel group (ms_per_step %.3f)" % (ms_single / args.steps),
         }
-        ms_val = ms_val_split
         # CPU baseline (bounded sample) — rank 0, N=1 only
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -495,6 +535,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-split", action="store_true", help="single-stream schedule for the headline region too (profiling runs: launches of one kernel back to back)")
     ap.add_argument("--chunk", type=int, default=None, help="frames per upload/compute chunk of the e2e path")
     ap.add_argument("--size", default=None, help="WxH override for ad-hoc runs (e.g. 1280x720); the default is the BASELINE metric's 640x480")
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step override (default 129)")

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RST_ABI_VERSION 1
+#define RST_ABI_VERSION 2
 #define RST_MAX_LEVELS 4
 
 /* ---- return codes of the API calls (call-level, not per-pair) ---- */
@@ -51,7 +51,7 @@ enum {
   RST_ERR_ARCH = 6          /* device is not sm_100 (B200)                 */
 };
 
-/* ---- per-pair status word (rst_stats.status), sticky over iterations ---- */
+/* ---- per-pair status bits (rst_stats.status: last evaluated iteration; rst_stats.any_status: sticky OR) ---- */
 enum {
   RST_STATUS_OK = 0,
   RST_STATUS_TOO_FEW = 1,    /* fewer than params.min_count associations
@@ -75,6 +75,17 @@ enum {
 enum {
   RST_TILING_THROUGHPUT = 0,  /* up to 8192 pixels per block: fewest partials, best for batches   */
   RST_TILING_LATENCY = 1      /* 512 pixels per block: a single pair spreads over all 148 SMs      */
+};
+
+/* ---- launch schedule of the iteration loop (rst_set_schedule) ---- */
+enum {
+  RST_SCHEDULE_AUTO = 0,           /* default: the schedule measured fastest on B200 (currently PER_ITERATION at every
+                                      batch size; never chosen by the batch size, so results stay bit-identical across
+                                      batch sizes)                                                                    */
+  RST_SCHEDULE_FUSED = 1,          /* one thread-block cluster per pair runs every iteration of every level in ONE
+                                      launch (partial sums combined through distributed shared memory)               */
+  RST_SCHEDULE_PER_ITERATION = 2,  /* one launch per iteration per level (block partials in global memory)           */
+  RST_SCHEDULE_HYBRID = 3          /* coarse levels fused (one launch), finest level one launch per iteration         */
 };
 
 /* Pin-hole intrinsics of the finest level; K = [[fx,0,cx],[0,fy,cy],[0,0,1]]
@@ -125,10 +136,14 @@ typedef struct rst_params {
  * iterate, i.e. the correspondences BEFORE the final update — the same
  * "pre-update" semantics as the reference's mean_cost (align_icp.cpp:104-113,157). */
 typedef struct rst_stats {
-  int32_t status;      /* RST_STATUS_* bit-or                                  */
-  int32_t iterations;  /* iterations executed                                   */
-  int32_t count;       /* associations in the last iteration                    */
-  float rmse;          /* sqrt(sum_wr2 / count) of the last iteration (m)       */
+  int32_t status;      /* RST_STATUS_* of the LAST evaluated iteration (plus NON_FINITE if the pose is not
+                          finite): the success criterion — a failed solve on a coarse level of sparse depth
+                          does not fail a pair whose fine levels converged                               */
+  int32_t iterations;  /* iterations executed (failed solves included)                                  */
+  int32_t count;       /* associations in the last iteration                                            */
+  float rmse;          /* sqrt(sum_wr2 / count) of the last iteration (m)                               */
+  int32_t any_status;  /* RST_STATUS_* bit-or over ALL iterations (sticky)                              */
+  int32_t failed_iterations; /* iterations whose solve failed (pose left unchanged by them)             */
   double sum_wr2;      /* sum w r^2                                             */
   double A[21];        /* upper triangle of J^T W J, row-major (0,0)..(5,5)     */
   double b[6];         /* J^T W r                                               */
@@ -202,6 +217,16 @@ int32_t rst_set_pipeline_chunk(rst_ctx* ctx, int32_t frames_per_chunk);
  * levels of the other. min_pairs <= 0 disables the split (single stream; used when timing one kernel in
  * isolation). Never changes results. */
 int32_t rst_set_stream_split(rst_ctx* ctx, int32_t min_pairs);
+
+/* Selects how the iteration loop is launched (RST_SCHEDULE_*). Poses agree between the two schedules to fp32
+ * round-off of the partial-sum extents; each schedule is bit-reproducible. */
+int32_t rst_set_schedule(rst_ctx* ctx, int32_t schedule);
+
+/* CTAs per pair of the fused kernel for a tiling (RST_TILING_*; defaults 4 and 8, at most 16). The cluster size
+ * fixes the partial-sum extents, so it is a property of the context, never of the batch. */
+int32_t rst_set_cluster_size(rst_ctx* ctx, int32_t tiling, int32_t ctas_per_pair);
+/* How many clusters of that size the device holds at once (pairs iterating concurrently); 0 on error. */
+int32_t rst_max_active_clusters(rst_ctx* ctx, int32_t ctas_per_pair);
 
 /* -------------------------------------------------------------------------
  * Staged / device-resident interface (what the two calls above are built from;
@@ -355,6 +380,9 @@ typedef struct rst_profile {
   int32_t launches_icp[RST_MAX_LEVELS];
   int64_t frames_preprocessed[RST_MAX_LEVELS]; /* frames covered by those launches      */
   int64_t pairs_iterated[RST_MAX_LEVELS];      /* sum over launches of pairs per launch */
+  float ms_icp_fused;                          /* fused schedule: whole iteration loop, summed since enable */
+  int32_t launches_icp_fused;
+  int64_t pair_iterations_fused;               /* sum over launches of pairs x iterations of all levels */
 } rst_profile;
 int32_t rst_profile_enable(rst_ctx* ctx, int32_t on); /* also resets the accumulators */
 int32_t rst_profile_read(rst_ctx* ctx, rst_profile* out); /* synchronises the stream  */

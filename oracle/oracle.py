@@ -27,7 +27,7 @@ class Params(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("status", C.c_int32), ("iterations", C.c_int32), ("count", C.c_int32), ("rmse", C.c_float),
-                ("sum_wr2", C.c_double), ("A", C.c_double * 21), ("b", C.c_double * 6)]
+                ("any_status", C.c_int32), ("failed_iterations", C.c_int32), ("sum_wr2", C.c_double), ("A", C.c_double * 21), ("b", C.c_double * 6)]
 
 
 class Level(C.Structure):

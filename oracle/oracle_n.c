@@ -393,7 +393,7 @@ static int32_t on_align_pair_impl(const uint16_t* src, const uint16_t* dst, cons
   }
   rst_stats s;
   memset(&s, 0, sizeof(s));
-  int32_t status = 0, iters = 0;
+  int32_t status = 0, any_status = 0, failed = 0, iters = 0;   /* status: last evaluated iteration; any_status: sticky OR */
   float cur[16];
   for (int l = nl - 1; l >= 0; --l) {
     int converged = 0;  /* per level: set once an update is smaller than converge_eps (0 = never) */
@@ -402,20 +402,21 @@ static int32_t on_align_pair_impl(const uint16_t* src, const uint16_t* dst, cons
       on_evaluate_impl(sD[l], sG[l], dG[l], sI[l], dI[l], &L[l], P, cur, NULL, &s);
       double xi[6];
       const int32_t rc = on_solve(s.A, s.b, s.count, P, xi);
+      status = rc;
       if (rc == RST_STATUS_OK) {
         on_pose_update(xi, Rt);
         const double wn = sqrt(xi[0] * xi[0] + xi[1] * xi[1] + xi[2] * xi[2]);
         const double vn = sqrt(xi[3] * xi[3] + xi[4] * xi[4] + xi[5] * xi[5]);
         if (P->converge_eps > 0.0f && wn < (double)P->converge_eps && vn < (double)P->converge_eps) converged = 1;
       } else {
-        status |= rc;
+        any_status |= rc; ++failed;
       }
       ++iters;
     }
   }
   rt_to_pose(Rt, pose);
-  for (int i = 0; i < 16; ++i) if (!isfinite(pose[i])) status |= RST_STATUS_NON_FINITE;
-  s.status = status; s.iterations = iters;
+  for (int i = 0; i < 16; ++i) if (!isfinite(pose[i])) { status |= RST_STATUS_NON_FINITE; any_status |= RST_STATUS_NON_FINITE; }
+  s.status = status; s.any_status = any_status; s.failed_iterations = failed; s.iterations = iters;
   if (st) *st = s;
   for (int l = 0; l < nl; ++l) { free(sD[l]); free(dD[l]); free(dG[l]); free(sG[l]); free(sI[l]); free(dI[l]); }
   return status;

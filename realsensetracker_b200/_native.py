@@ -46,7 +46,7 @@ class Params(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("status", C.c_int32), ("iterations", C.c_int32), ("count", C.c_int32), ("rmse", C.c_float),
-                ("sum_wr2", C.c_double), ("A", C.c_double * 21), ("b", C.c_double * 6)]
+                ("any_status", C.c_int32), ("failed_iterations", C.c_int32), ("sum_wr2", C.c_double), ("A", C.c_double * 21), ("b", C.c_double * 6)]
 
 
 class Cloud(C.Structure):
@@ -61,7 +61,8 @@ class Icp3dResult(C.Structure):
 class Profile(C.Structure):
     _fields_ = [("ms_preprocess", C.c_float * RST_MAX_LEVELS), ("ms_icp", C.c_float * RST_MAX_LEVELS),
                 ("launches_preprocess", C.c_int32 * RST_MAX_LEVELS), ("launches_icp", C.c_int32 * RST_MAX_LEVELS),
-                ("frames_preprocessed", C.c_int64 * RST_MAX_LEVELS), ("pairs_iterated", C.c_int64 * RST_MAX_LEVELS)]
+                ("frames_preprocessed", C.c_int64 * RST_MAX_LEVELS), ("pairs_iterated", C.c_int64 * RST_MAX_LEVELS),
+                ("ms_icp_fused", C.c_float), ("launches_icp_fused", C.c_int32), ("pair_iterations_fused", C.c_int64)]
 
 
 # every symbol include/rst_align.h declares (tests check the library exports all of them)
@@ -71,6 +72,7 @@ ALIGN_SYMBOLS = [
     "rst_set_frames_device", "rst_preprocess", "rst_align_slots", "rst_device_results", "rst_sync",
     "rst_level_info", "rst_read_depth", "rst_read_geometry", "rst_read_intensity", "rst_evaluate", "rst_launch_count",
     "rst_copy_results_device", "rst_profile_enable", "rst_profile_read", "rst_set_pipeline_chunk", "rst_set_stream_split", "rst_align_pairs_async", "rst_align_sequence_async", "rst_wait", "rst_icp3d_pairs", "rst_solve_kabsch", "rst_cloud_normals", "rst_icp3d_depth", "rst_icp3d_read_cloud",
+    "rst_set_schedule", "rst_set_cluster_size", "rst_max_active_clusters",
 ]
 
 _align = None
@@ -159,6 +161,12 @@ def align_lib() -> C.CDLL:
         lib.rst_copy_results_device.restype = C.c_int32
         lib.rst_set_stream_split.argtypes = [C.c_void_p, C.c_int32]
         lib.rst_set_stream_split.restype = C.c_int32
+        lib.rst_set_schedule.argtypes = [C.c_void_p, C.c_int32]
+        lib.rst_set_schedule.restype = C.c_int32
+        lib.rst_set_cluster_size.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        lib.rst_set_cluster_size.restype = C.c_int32
+        lib.rst_max_active_clusters.argtypes = [C.c_void_p, C.c_int32]
+        lib.rst_max_active_clusters.restype = C.c_int32
         lib.rst_set_pipeline_chunk.argtypes = [C.c_void_p, C.c_int32]
         lib.rst_set_pipeline_chunk.restype = C.c_int32
         lib.rst_profile_enable.argtypes = [C.c_void_p, C.c_int32]

@@ -276,6 +276,16 @@ class Aligner:
     def set_stream_split(self, min_pairs: int):
         self._check(self._lib.rst_set_stream_split(self._ctx, min_pairs))
 
+    def set_schedule(self, schedule: int):
+        """0 = fused (one cluster per pair, all iterations in one launch; default), 1 = one launch per iteration."""
+        self._check(self._lib.rst_set_schedule(self._ctx, schedule))
+
+    def set_cluster_size(self, tiling: int, ctas_per_pair: int):
+        self._check(self._lib.rst_set_cluster_size(self._ctx, tiling, ctas_per_pair))
+
+    def max_active_clusters(self, ctas_per_pair: int) -> int:
+        return int(self._lib.rst_max_active_clusters(self._ctx, ctas_per_pair))
+
     def set_pipeline_chunk(self, frames_per_chunk: int):
         self._check(self._lib.rst_set_pipeline_chunk(self._ctx, frames_per_chunk))
 

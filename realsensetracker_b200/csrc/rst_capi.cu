@@ -8,6 +8,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -52,6 +53,7 @@ struct rst_ctx {
   const uint16_t* ext_depth0 = nullptr;
   int ext_pitch0 = 0;
   int64_t ext_frame0 = 0;
+  int ext_first = 0, ext_count = 0;     // slots [ext_first, ext_first + ext_count) are backed by the caller's memory
   bool store_dirty = true;
 
   // pair state (max_pairs + 1: the last entry is the rst_evaluate scratch pair)
@@ -75,6 +77,8 @@ struct rst_ctx {
 
   cudaStream_t copy_stream = nullptr;   // H2D of the next chunk overlaps compute of the current one
   cudaStream_t work_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // chunks alternate between two compute streams
+  int schedule = RST_SCHEDULE_AUTO;     // see rst_set_schedule
+  int cluster_size[2] = {4, 8};         // CTAs per pair of the fused kernel, by rst_params.tiling (throughput, latency)
   int split_ways = 2;                   // measured on B200: 2, 3 and 4 ways are equal (2.18 ms per 128-pair step)
   int split_min_pairs = 32;             // batches of at least this many pairs iterate as two halves on two streams
   int pipeline_chunk = 0;               // frames (pairs) per upload/compute chunk of the host entry points
@@ -99,7 +103,7 @@ static cudaEvent_t prof_event(rst_ctx* c) {
   else cudaEventCreate(&e);
   return e;
 }
-/* kind 0 = preprocess, 1 = icp */
+/* kind 0 = preprocess, 1 = icp (per-iteration schedule, by level), 2 = fused icp */
 static int prof_begin(rst_ctx* c, int kind, int level) {
   if (!c->profiling) return -1;
   rst_ctx::ProfRec r{kind, level, 0, 0, prof_event(c), prof_event(c)};
@@ -205,8 +209,9 @@ int32_t rst_ctx_create(int32_t device, int32_t max_w, int32_t max_h, int32_t max
   g_create_err.clear();
   if (!out) { g_create_err = "out_ctx is null"; return RST_ERR_INVALID_ARG; }
   *out = nullptr;
-  if (max_w < 16 || max_h < 16 || max_frames < 2 || max_pairs < 1 || max_w > 16384 || max_h > 16384) {
-    g_create_err = "bad capacity (need max_w,max_h >= 16, max_frames >= 2, max_pairs >= 1)";
+  if (max_w < 16 || max_h < 16 || max_frames < 2 || max_pairs < 1 || max_w > 16384 || max_h > 16384 ||
+      (int64_t)max_w * max_h > (1ll << 27)) {  // texel byte offsets inside a frame are 32-bit
+    g_create_err = "bad capacity (need 16 <= max_w,max_h <= 16384, max_w*max_h <= 2^27, max_frames >= 2, max_pairs >= 1)";
     return RST_ERR_INVALID_ARG;
   }
   int n_dev = 0;
@@ -272,6 +277,14 @@ int32_t rst_ctx_create(int32_t device, int32_t max_w, int32_t max_h, int32_t max
   CREATE_TRY(cudaMallocHost(&c->h_poses, sizeof(float) * 16 * np));
   CREATE_TRY(cudaMallocHost(&c->h_stats, sizeof(rst_stats) * np));
 #undef CREATE_TRY
+  if (const char* e = std::getenv("RST_FUSED_CLUSTER")) {   // experiments: CTAs per pair of the fused kernel
+    const int v = std::atoi(e);
+    if (v >= 1 && v <= 16) c->cluster_size[0] = c->cluster_size[1] = v;
+  }
+  if (const char* e = std::getenv("RST_SCHEDULE")) {
+    const int v = std::atoi(e);
+    if (v >= RST_SCHEDULE_AUTO && v <= RST_SCHEDULE_HYBRID) c->schedule = v;
+  }
   *out = c;
   return RST_OK;
 }
@@ -336,7 +349,7 @@ int32_t rst_begin(rst_ctx* c, int32_t width, int32_t height, const rst_intrinsic
     }
     c->store_dirty = false;
   }
-  c->ext0 = false; c->ext_depth0 = nullptr;
+  c->ext0 = false; c->ext_depth0 = nullptr; c->ext_first = 0; c->ext_count = 0;
   c->photo = P.photo_weight > 0.0f;
   if (c->photo && !c->d_rgb) {
     RST_CUDA(c, cudaMalloc(&c->d_rgb, (size_t)c->max_w * c->max_h * 3 * c->max_frames));
@@ -410,6 +423,23 @@ int32_t rst_set_frames_device(rst_ctx* c, const uint16_t* d_depth, int32_t n, in
   c->ext_depth0 = d_depth - (int64_t)first_slot * frame_stride_px;
   c->ext_pitch0 = row_stride_px;
   c->ext_frame0 = frame_stride_px;
+  c->ext_first = first_slot;
+  c->ext_count = n;
+  return RST_OK;
+}
+
+/* while level 0 is read in place from caller memory only the bound slots exist */
+static bool slot_bound(const rst_ctx* c, int slot) {
+  if (slot < 0 || slot >= c->max_frames) return false;
+  return !c->ext0 || (slot >= c->ext_first && slot < c->ext_first + c->ext_count);
+}
+
+/* one outstanding *_async call per context: its results sit in the pinned staging until rst_wait */
+static int32_t check_idle(rst_ctx* c) {
+  if (c->fetch_pending != 0) {
+    c->err = "an asynchronous call is outstanding on this context: call rst_wait first";
+    return RST_ERR_INVALID_ARG;
+  }
   return RST_OK;
 }
 
@@ -462,6 +492,8 @@ int32_t rst_preprocess(rst_ctx* c, int32_t first_slot, int32_t n) {
   if (!c) return RST_ERR_INVALID_ARG;
   if (!c->begun) return fail(c, RST_ERR_INVALID_ARG, "rst_begin has not been called");
   if (first_slot < 0 || n < 0 || first_slot + n > c->max_frames) return fail(c, RST_ERR_CAPACITY, "slot range out of capacity");
+  if (n > 0 && (!slot_bound(c, first_slot) || !slot_bound(c, first_slot + n - 1)))
+    return fail(c, RST_ERR_INVALID_ARG, "slot range outside the frames bound by rst_set_frames_device");
   RST_CUDA(c, cudaSetDevice(c->device));
   return preprocess_impl(c, first_slot, n, true);
 }
@@ -483,6 +515,7 @@ static void fill_icp_args(const rst_ctx* c, int l, IcpArgs* a) {
   a->group_du = (kChunksPerBlock % c->chunks_per_row[l]) * kChunkPx;
   a->cpr_magic = (uint32_t)(((1ull << 32) + (uint64_t)c->chunks_per_row[l] - 1) / (uint64_t)c->chunks_per_row[l]);
   a->d_lo = c->d_lo; a->d_span = c->d_span;
+  a->guard_texel = (uint32_t)(c->geom[l].w * c->geom[l].h);
   a->umax = (float)c->geom[l].w - 0.5f; a->vmax = (float)c->geom[l].h - 0.5f;
   a->depth_scale = c->P.depth_scale;
   a->dmax2 = c->P.dist_max * c->P.dist_max;
@@ -518,9 +551,10 @@ static int32_t link_streams(rst_ctx* c, cudaStream_t from, cudaStream_t to) {  /
 /* stage 1 of an alignment: pair table + initial poses -> device, state reset */
 static int32_t pairs_begin(rst_ctx* c, const int32_t* src_slots, const int32_t* dst_slots, int32_t n_pairs,
                            const float* poses_in) {
+  if (check_idle(c) != RST_OK) return RST_ERR_INVALID_ARG;   // the pinned staging below still belongs to that call
   for (int i = 0; i < n_pairs; ++i) {
-    if (src_slots[i] < 0 || src_slots[i] >= c->max_frames || dst_slots[i] < 0 || dst_slots[i] >= c->max_frames)
-      return fail(c, RST_ERR_INVALID_ARG, "slot index out of range");
+    if (!slot_bound(c, src_slots[i]) || !slot_bound(c, dst_slots[i]))
+      return fail(c, RST_ERR_INVALID_ARG, "slot index out of range (or outside the frames bound by rst_set_frames_device)");
     c->h_pairs[i] = make_int2(src_slots[i], dst_slots[i]);
   }
   if (poses_in) {
@@ -538,11 +572,63 @@ static int32_t pairs_begin(rst_ctx* c, const int32_t* src_slots, const int32_t* 
   return RST_OK;
 }
 
+/* stage 2, fused schedule: ONE launch runs every iteration of every level for pairs [first, first + n);
+ * a cluster of cluster_size[tiling] CTAs owns each pair (csrc/rst_icp_kernels.cu, k_icp_fused). The cluster size
+ * depends on the tiling switch only — never on the batch — so results are bit-identical across batch sizes. */
+static int32_t pairs_iterate_fused(rst_ctx* c, int first, int n, int level_hi, int level_lo) {
+  const int C = c->cluster_size[c->P.tiling == RST_TILING_LATENCY ? 1 : 0];
+  FusedArgs a{};
+  for (int l = 0; l < c->num_levels; ++l) {
+    FusedLevel& L = a.lvl[l];
+    L.g = c->geom[l];
+    L.lv = level_store(c, l);
+    L.chunks_per_row = c->chunks_per_row[l];
+    L.n_groups = (c->n_chunks[l] + kChunksPerBlock - 1) / kChunksPerBlock;
+    L.groups_per_cta = (L.n_groups + C - 1) / C;
+    L.group_dv = kChunksPerBlock / c->chunks_per_row[l];
+    L.group_du = (kChunksPerBlock % c->chunks_per_row[l]) * kChunkPx;
+    L.iters = c->P.iters[l];
+    L.cpr_magic = (uint32_t)(((1ull << 32) + (uint64_t)c->chunks_per_row[l] - 1) / (uint64_t)c->chunks_per_row[l]);
+    L.guard_texel = (uint32_t)(c->geom[l].w * c->geom[l].h);
+  }
+  a.level_hi = level_hi; a.level_lo = level_lo;
+  a.pairs = c->d_pairs;
+  a.pose_f32 = c->d_pose_f32; a.pose_master = c->d_master; a.poses_cm = c->d_poses_cm; a.stats = c->d_stats;
+  a.d_lo = c->d_lo; a.d_span = c->d_span;
+  a.depth_scale = c->P.depth_scale; a.dmax2 = c->P.dist_max * c->P.dist_max; a.ncos_min = c->P.normal_cos_min;
+  a.robust_scale = c->P.robust_scale; a.sqrt_lambda = sqrtf(c->P.photo_weight);
+  a.min_count = c->P.min_count; a.damping = c->P.damping; a.converge_eps = c->P.converge_eps;
+  const bool ngate = c->P.normal_cos_min > -1.0f;
+  int iters_total = 0;
+  for (int l = level_lo; l <= level_hi; ++l) iters_total += c->P.iters[l];
+  if (iters_total == 0) return RST_OK;
+  const int ph = prof_begin(c, 2, 0);
+  int nl = 0;
+  for (int off = 0; off < n; off += 65535) {
+    a.pair_offset = first + off;
+    const int cnt = n - off < 65535 ? n - off : 65535;
+    RST_CUDA(c, launch_icp_fused(a, cnt, C, c->P.robust_kind, ngate, c->photo, c->stream));
+    c->launches += 1;
+    ++nl;
+  }
+  prof_end(c, ph, nl, (int64_t)n * iters_total);
+  return RST_OK;
+}
+
 /* stage 2: the whole coarse-to-fine schedule for pairs [first, first + n) */
 static int32_t pairs_iterate(rst_ctx* c, int first, int n) {
   if (n <= 0) return RST_OK;
+  // which levels run inside the fused cluster kernel (the rest: one launch per iteration)
+  int fused_lo = c->num_levels;   // none
+  if (c->schedule == RST_SCHEDULE_FUSED) fused_lo = 0;
+  else if (c->schedule == RST_SCHEDULE_HYBRID) fused_lo = 1;
+  // RST_SCHEDULE_AUTO: one launch per iteration — measured fastest on B200 at every batch size tried
+  if (fused_lo < c->num_levels) {
+    const int32_t rc = pairs_iterate_fused(c, first, n, c->num_levels - 1, fused_lo);
+    if (rc != RST_OK) return rc;
+  }
   const bool ngate = c->P.normal_cos_min > -1.0f;
-  for (int l = c->num_levels - 1; l >= 0; --l) {
+  for (int l = fused_lo - 1; l >= 0; --l) {
     IcpArgs a{};
     fill_icp_args(c, l, &a);
     if (a.done) RST_CUDA(c, cudaMemsetAsync(c->d_done + first, 0, (size_t)n, c->stream));  // every level starts active
@@ -566,7 +652,8 @@ static int32_t pairs_iterate(rst_ctx* c, int first, int n) {
  * launches of one half fill the partial last wave (and the latency-bound coarse levels) of the other.
  * Pairs are independent and reduced in image-size-determined blocks, so the split never changes a bit. */
 static int32_t pairs_iterate_split(rst_ctx* c, int n_pairs) {
-  if (n_pairs < c->split_min_pairs) return pairs_iterate(c, 0, n_pairs);
+  // the fused schedule is one launch whose clusters are all resident at once: nothing to interleave
+  if (c->schedule == RST_SCHEDULE_FUSED || n_pairs < c->split_min_pairs) return pairs_iterate(c, 0, n_pairs);
   cudaStream_t main_s = c->stream;
   const int ways = c->split_ways;
   const int part = (n_pairs + ways - 1) / ways;
@@ -628,6 +715,28 @@ int32_t rst_set_stream_split(rst_ctx* c, int32_t min_pairs) {
   return RST_OK;
 }
 
+int32_t rst_set_schedule(rst_ctx* c, int32_t schedule) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  if (schedule < RST_SCHEDULE_AUTO || schedule > RST_SCHEDULE_HYBRID) return fail(c, RST_ERR_INVALID_ARG, "unknown schedule");
+  c->schedule = schedule;
+  return RST_OK;
+}
+
+int32_t rst_set_cluster_size(rst_ctx* c, int32_t tiling, int32_t ctas_per_pair) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  if (tiling < 0 || tiling > 1 || ctas_per_pair < 1 || ctas_per_pair > 16) return fail(c, RST_ERR_INVALID_ARG, "tiling must be 0/1, ctas_per_pair 1..16");
+  RST_CUDA(c, cudaSetDevice(c->device));
+  if (fused_max_active_clusters(ctas_per_pair) < 1) return fail(c, RST_ERR_INVALID_ARG, "this device cannot co-schedule a cluster of that size");
+  c->cluster_size[tiling] = ctas_per_pair;
+  return RST_OK;
+}
+
+int32_t rst_max_active_clusters(rst_ctx* c, int32_t ctas_per_pair) {
+  if (!c || ctas_per_pair < 1 || ctas_per_pair > 16) return 0;
+  if (cudaSetDevice(c->device) != cudaSuccess) return 0;
+  return fused_max_active_clusters(ctas_per_pair);
+}
+
 int32_t rst_set_pipeline_chunk(rst_ctx* c, int32_t frames_per_chunk) {
   if (!c) return RST_ERR_INVALID_ARG;
   c->pipeline_chunk = frames_per_chunk > 0 ? frames_per_chunk : 0;
@@ -672,6 +781,7 @@ int32_t rst_profile_read(rst_ctx* c, rst_profile* out) {
     float ms = 0.f;
     RST_CUDA(c, cudaEventElapsedTime(&ms, r.e0, r.e1));
     if (r.kind == 0) { c->prof.ms_preprocess[r.level] += ms; c->prof.launches_preprocess[r.level] += r.launches; c->prof.frames_preprocessed[r.level] += r.units; }
+    else if (r.kind == 2) { c->prof.ms_icp_fused += ms; c->prof.launches_icp_fused += r.launches; c->prof.pair_iterations_fused += r.units; }
     else { c->prof.ms_icp[r.level] += ms; c->prof.launches_icp[r.level] += r.launches; c->prof.pairs_iterated[r.level] += r.units; }
     c->ev_pool.push_back(r.e0); c->ev_pool.push_back(r.e1);
   }
@@ -705,6 +815,7 @@ static int32_t align_pairs_impl(rst_ctx* c, const rst_frame* src, const rst_fram
   if (!c) return RST_ERR_INVALID_ARG;
   if (!src || !dst || n_pairs < 0 || (wait && !poses_inout)) return fail(c, RST_ERR_INVALID_ARG, "null src/dst/poses or negative n_pairs");
   if (n_pairs == 0) return RST_OK;
+  if (check_idle(c) != RST_OK) return RST_ERR_INVALID_ARG;
   if (2 * (int64_t)n_pairs > c->max_frames || n_pairs > c->max_pairs) return fail(c, RST_ERR_CAPACITY, "batch exceeds the context capacity");
   int32_t rc;
   if ((rc = check_frames(c, src, n_pairs)) != RST_OK) return rc;
@@ -758,6 +869,7 @@ static int32_t align_sequence_impl(rst_ctx* c, const rst_frame* frames, int32_t 
   if (!c) return RST_ERR_INVALID_ARG;
   if (!frames || n_frames < 0 || (wait && !poses_inout)) return fail(c, RST_ERR_INVALID_ARG, "null frames/poses or negative n_frames");
   if (n_frames < 2) return RST_OK;
+  if (check_idle(c) != RST_OK) return RST_ERR_INVALID_ARG;
   if (n_frames > c->max_frames || n_frames - 1 > c->max_pairs) return fail(c, RST_ERR_CAPACITY, "sequence exceeds the context capacity");
   int32_t rc;
   if ((rc = check_frames(c, frames, n_frames)) != RST_OK) return rc;
@@ -862,8 +974,9 @@ int32_t rst_evaluate(rst_ctx* c, int32_t src_slot, int32_t dst_slot, int32_t lev
                      int32_t* idx_out, rst_stats* stats_out) {
   if (!c) return RST_ERR_INVALID_ARG;
   if (!c->begun || !pose || !stats_out || level < 0 || level >= c->num_levels) return fail(c, RST_ERR_INVALID_ARG, "bad level/pose/stats");
-  if (src_slot < 0 || src_slot >= c->max_frames || dst_slot < 0 || dst_slot >= c->max_frames)
-    return fail(c, RST_ERR_INVALID_ARG, "slot index out of range");
+  if (!slot_bound(c, src_slot) || !slot_bound(c, dst_slot))
+    return fail(c, RST_ERR_INVALID_ARG, "slot index out of range (or outside the frames bound by rst_set_frames_device)");
+  if (check_idle(c) != RST_OK) return RST_ERR_INVALID_ARG;
   RST_CUDA(c, cudaSetDevice(c->device));
   const int sp = c->max_pairs;  // scratch pair
   c->h_pairs[sp] = make_int2(src_slot, dst_slot);

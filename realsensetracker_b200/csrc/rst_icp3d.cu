@@ -161,7 +161,7 @@ __device__ void nn_search(const Grid& g, const int* __restrict__ cell_start, con
   const int cx = cell_coord(px, g.lox, g.inv_h, g.nx), cy = cell_coord(py, g.loy, g.inv_h, g.ny),
             cz = cell_coord(pz, g.loz, g.inv_h, g.nz);
   float bd = FLT_MAX;
-  int bj = 0x7fffffff;
+  int bj = 0;  // always a valid index: a query that beats nothing (non-finite coordinates) must not return INT_MAX
   for (int r = 0;; ++r) {
     const int x0 = max(cx - r, 0), x1 = min(cx + r, g.nx - 1);
     const int y0 = max(cy - r, 0), y1 = min(cy + r, g.ny - 1);
@@ -358,7 +358,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
       const float py = addrn(addrn(addrn(mulrn(T[1], sx), mulrn(T[4], sy)), mulrn(T[7], sz)), T[10]);
       const float pz = addrn(addrn(addrn(mulrn(T[2], sx), mulrn(T[5], sy)), mulrn(T[8], sz)), T[11]);
       int j; float d2;
-      if (iter == 0) nn_search(g, P.cell_start, P.sorted, px, py, pz, &j, &d2);
+      // a non-finite source point or pose (the reference's callers run RemoveNans first) has no neighbour:
+      // index 0, d2 = +inf, hence weight 0, cost = inf and ok = 0 — without walking the whole grid for it
+      if (!(isfinite(px) && isfinite(py) && isfinite(pz))) { j = 0; d2 = __int_as_float(0x7f800000); }
+      else if (iter == 0) nn_search(g, P.cell_start, P.sorted, px, py, pz, &j, &d2);
       else nn_refine(g, P.cell_start, P.sorted, P.dst, px, py, pz, P.nbr[i], &j, &d2);
       const float rt = __fdiv_rn(mu, addrn(d2, mu));
       P.nbr[i] = j;

@@ -4,11 +4,15 @@
  *   K1+K2+K6  k_preprocess : uint16 depth tile (+1 px halo) -> shared memory via 128-bit
  *                            loads; back-projection, normals -> geometry map float4
  *                            {nx,ny,nz,z}; 2x2 integer pooling -> next pyramid level.
- *   K3+K4+K5  k_icp_iter   : projective association + point-to-plane residual/Jacobian,
- *                            29 sums per thread -> warp shuffle tree -> block tree ->
- *                            per-block partials -> last block of each pair (ticket) sums
- *                            them in fixed order in fp64, solves the 6x6 system by
- *                            Cholesky and updates the pose on the device.
+ *   K3+K4+K5  k_icp_fused  : one thread-block cluster per pair, every iteration of every level
+ *                            in ONE launch: projective association + point-to-plane
+ *                            residual/Jacobian, 29 sums per thread -> warp shuffle tree ->
+ *                            block tree -> cluster totals through distributed shared memory in
+ *                            fixed rank order (fp64) -> 6x6 Cholesky + SE(3) update on the
+ *                            leader CTA -> pose of the next iteration back through DSMEM.
+ *             k_icp_iter   : the same pixel pipeline, one launch per iteration (block partials
+ *                            in global memory, last block of a pair reduces and solves);
+ *                            rst_evaluate and the per-iteration schedule.
  *   k_init_pairs           : pose upload -> fp64 master pose, state reset.
  *
  * Nearest reference counterparts: align_icp.cpp:101-151 (correspondence loop,
@@ -33,7 +37,10 @@ constexpr int kAccPad = 32;       // partial row stride (floats)
 #define RST_ICP_CPW 2
 #endif
 #ifndef RST_ICP_MINB
-#define RST_ICP_MINB 5
+#define RST_ICP_MINB 4            // resident blocks per SM k_icp_iter is compiled for: 4 -> 128 registers, no spills (5 -> 96: 1.5 % slower)
+#endif
+#ifndef RST_FUSED_MINB
+#define RST_FUSED_MINB 4          // resident CTAs per SM the fused kernel is compiled for (4 -> 128 registers per thread)
 #endif
 #ifndef RST_ICP_GROUP_PX
 #define RST_ICP_GROUP_PX 8192     // pixels per block on large levels (groups = this / block pixels per group)
@@ -91,6 +98,7 @@ struct IcpArgs {
   int32_t group_dv, group_du; // kChunksPerBlock chunks = group_dv rows + group_du columns
   uint32_t cpr_magic;         // ceil(2^32 / chunks_per_row): c / chunks_per_row == umulhi(c, magic)
   uint32_t d_lo, d_span;      // valid raw depth: (d - d_lo) <= d_span  <=>  d != 0 && z_min <= d*scale <= z_max
+  uint32_t guard_texel;       // w * h: index of the all-zero texel behind every geometry frame (gather target of rejected pixels)
   float umax, vmax;           // w - 0.5, h - 0.5
   float depth_scale, dmax2, ncos_min, robust_scale;
   float sqrt_lambda;          // sqrt(photo_weight), photometric variant only
@@ -107,6 +115,35 @@ struct IcpArgs {
   int32_t* idx_out;           // WRITE_IDX: [pair-local][h*w]
 };
 
+/* one pyramid level as the fused kernel sees it */
+struct FusedLevel {
+  LevelGeom g;
+  LevelStore lv;
+  int32_t chunks_per_row;
+  int32_t n_groups;           // groups of kChunksPerBlock chunks covering the level
+  int32_t groups_per_cta;     // ceil(n_groups / cluster size): contiguous share of one CTA
+  int32_t group_dv, group_du; // kChunksPerBlock chunks = group_dv rows + group_du columns
+  int32_t iters;              // iterations on this level
+  uint32_t cpr_magic;         // ceil(2^32 / chunks_per_row)
+  uint32_t guard_texel;       // w * h
+};
+
+/* k_icp_fused: every iteration of levels level_hi .. level_lo of a batch of pairs, one cluster per pair */
+struct FusedArgs {
+  FusedLevel lvl[RST_MAX_LEVELS];
+  int32_t level_hi, level_lo;
+  const int2* pairs;          // (src slot, dst slot)
+  int32_t pair_offset;
+  float* pose_f32;            // 12 per pair, in: pose of the first iteration, out: final
+  double* pose_master;        // 12 per pair, in/out
+  float* poses_cm;            // 16 per pair, column-major 4x4 result
+  rst_stats* stats;           // in: reset by k_init_pairs, out: last evaluated iterate
+  uint32_t d_lo, d_span;
+  float depth_scale, dmax2, ncos_min, robust_scale, sqrt_lambda;
+  int32_t min_count;
+  float damping, converge_eps;
+};
+
 struct InitArgs {
   const float* poses_cm_in;   // 16 per pair
   double* pose_master;
@@ -120,6 +157,9 @@ struct InitArgs {
 cudaError_t launch_preprocess(const PreArgs& a, int n_frames, cudaStream_t s);
 cudaError_t launch_icp_iter(const IcpArgs& a, int n_pairs, int robust_kind, bool normal_gate,
                             bool write_idx, bool photo, cudaStream_t s);
+cudaError_t launch_icp_fused(const FusedArgs& a, int n_pairs, int cluster, int robust_kind, bool normal_gate,
+                             bool photo, cudaStream_t s);
+int fused_max_active_clusters(int cluster);
 
 /* f2: grey intensity (level 0 from CV_8UC3 RGB, then 2x2 means) */
 struct IntensityArgs {

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     assert sorted(N.ALIGN_SYMBOLS) == names, "ALIGN_SYMBOLS is out of sync with the header"
-    assert lib.rst_abi_version() == 1
+    assert lib.rst_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header(tmp_path):
