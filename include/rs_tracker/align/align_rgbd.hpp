@@ -182,7 +182,109 @@ inline bool SolveKabsch(AlignContext& ctx, const Cloud& src, const Cloud& dst, c
   return rc == RST_OK && ok != 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Cloud utilities of rs_tracker/common/point_cloud_utils.hpp:11-31 on the GPU, same signatures. `Cloud` as above,
+// plus SetNumPoints(n) and a mutable GetPtr() for outputs (cho::core::PointCloud has both).
+// ------------------------------------------------------------------------------------------------
+
+/// void DownsampleVoxel(cloud_in, voxel_size, &cloud_out)  point_cloud_utils.cpp:34-68 (cloud_out may alias cloud_in).
+template <class Cloud>
+inline void DownsampleVoxel(AlignContext& ctx, const Cloud& cloud_in, const float voxel_size, Cloud* const cloud_out) {
+  const rst_cloud in{cloud_in.GetPtr(), static_cast<std::int32_t>(cloud_in.GetNumPoints())};
+  std::vector<float> out(3 * static_cast<std::size_t>(in.n));
+  std::int32_t n = 0;
+  if (rst_downsample_voxel(ctx.get(), &in, voxel_size, out.data(), &n) != RST_OK) n = 0;
+  cloud_out->SetNumPoints(n);
+  if (n) std::memcpy(cloud_out->GetPtr(), out.data(), sizeof(float) * 3 * static_cast<std::size_t>(n));
+}
+
+/// void RemoveNans(cloud_in, &cloud_out)  point_cloud_utils.cpp:163-174.
+template <class Cloud>
+inline void RemoveNans(AlignContext& ctx, const Cloud& cloud_in, Cloud* const cloud_out) {
+  const rst_cloud in{cloud_in.GetPtr(), static_cast<std::int32_t>(cloud_in.GetNumPoints())};
+  std::vector<float> out(3 * static_cast<std::size_t>(in.n));
+  std::int32_t n = 0;
+  if (rst_remove_nans(ctx.get(), &in, out.data(), &n) != RST_OK) n = 0;
+  cloud_out->SetNumPoints(n);
+  if (n) std::memcpy(cloud_out->GetPtr(), out.data(), sizeof(float) * 3 * static_cast<std::size_t>(n));
+}
+
+/// void FindCorrespondences(tree, source, &indices, &squared_distances)  point_cloud_utils.cpp:70-90; `target` is the
+/// cloud the reference's KDTree3f was built over.
+template <class Cloud>
+inline void FindCorrespondences(AlignContext& ctx, const Cloud& target, const Cloud& source, std::vector<int>* const indices,
+                                std::vector<float>* const squared_distances) {
+  const rst_cloud t{target.GetPtr(), static_cast<std::int32_t>(target.GetNumPoints())};
+  const rst_cloud s{source.GetPtr(), static_cast<std::int32_t>(source.GetNumPoints())};
+  static_assert(sizeof(int) == sizeof(std::int32_t), "int must be 32-bit");
+  indices->assign(static_cast<std::size_t>(s.n), -1);
+  squared_distances->assign(static_cast<std::size_t>(s.n), 0.f);
+  if (s.n) rst_find_correspondences(ctx.get(), &t, &s, /*grid_cell=*/0.f, indices->data(), squared_distances->data());
+}
+
+/// The process-wide context the literal (context-free) signatures below run on: created on first use on CUDA device
+/// RS_TRACKER_ALIGN_DEVICE (default 0). The cloud engine sizes its own device memory per call, so the frame capacity
+/// of this context is minimal; use an explicit AlignContext for the frame-based calls.
+#ifndef RS_TRACKER_ALIGN_DEVICE
+#define RS_TRACKER_ALIGN_DEVICE 0
+#endif
+inline AlignContext& DefaultAlignContext() {
+  static AlignContext ctx(RS_TRACKER_ALIGN_DEVICE, 16, 16, 2, 1);
+  return ctx;
+}
+
 #ifdef RS_TRACKER_HAVE_EIGEN
+// ------------------------------------------------------------------------------------------------
+// The reference's LITERAL signatures (align_icp.hpp:14-24, point_cloud_utils.hpp:11-31): the call sites
+// rs_replay_app.cpp:246-251 and rs_align_app.cpp:295,303 compile against this header unchanged.
+// ------------------------------------------------------------------------------------------------
+namespace detail {
+inline Pose ToPose(const Eigen::Isometry3f& x) { Pose p; std::memcpy(p.m.data(), x.matrix().data(), sizeof(float) * 16); return p; }
+inline void FromPose(const Pose& p, Eigen::Isometry3f* const x) { std::memcpy(x->matrix().data(), p.m.data(), sizeof(float) * 16); }
+}  // namespace detail
+
+/// bool AlignIcp3d(const Cloud3f& src, const Cloud3f& dst, const int max_iter, Eigen::Isometry3f* const transform)
+template <class Cloud>
+inline bool AlignIcp3d(const Cloud& src, const Cloud& dst, const int max_iter, Eigen::Isometry3f* const transform) {
+  Pose p = detail::ToPose(*transform);   // read as the initial guess (align_icp.cpp:82)
+  const bool ok = AlignIcp3d(DefaultAlignContext(), src, dst, max_iter, &p);
+  detail::FromPose(p, transform);        // overwritten with the result (:156)
+  return ok;
+}
+
+/// bool AlignIcp3d(src, dst, const KDTree3f& dst_tree, max_iter, transform): the tree is the reference's search
+/// structure over `dst`; the GPU builds its own grid over `dst`, so it is accepted and not used.
+template <class Cloud, class Tree>
+inline bool AlignIcp3d(const Cloud& src, const Cloud& dst, const Tree& /*dst_tree*/, const int max_iter,
+                       Eigen::Isometry3f* const transform) {
+  return AlignIcp3d(src, dst, max_iter, transform);
+}
+
+/// bool SolveKabsch(src, dst, indices, weights, Eigen::Isometry3f* const xfm)
+template <class Cloud>
+inline bool SolveKabsch(const Cloud& src, const Cloud& dst, const std::vector<std::pair<int, int>>& indices,
+                        const std::vector<float>& weights, Eigen::Isometry3f* const xfm) {
+  Pose p;
+  const bool ok = SolveKabsch(DefaultAlignContext(), src, dst, indices, weights, &p);
+  if (ok) detail::FromPose(p, xfm);
+  return ok;
+}
+
+template <class Cloud>
+inline void DownsampleVoxel(const Cloud& cloud_in, const float voxel_size, Cloud* const cloud_out) {
+  DownsampleVoxel(DefaultAlignContext(), cloud_in, voxel_size, cloud_out);
+}
+template <class Cloud>
+inline void RemoveNans(const Cloud& cloud_in, Cloud* const cloud_out) {
+  RemoveNans(DefaultAlignContext(), cloud_in, cloud_out);
+}
+/// void FindCorrespondences(const KDTree3f& tree, const Cloud3f& source, ...): the tree names its cloud (kdtree.hpp:43).
+template <class Tree, class Cloud>
+inline auto FindCorrespondences(const Tree& tree, const Cloud& source, std::vector<int>* const indices,
+                                std::vector<float>* const squared_distances) -> decltype(tree.m_cloud.get(), void()) {
+  FindCorrespondences(DefaultAlignContext(), tree.m_cloud.get(), source, indices, squared_distances);
+}
+
 /// Drop-in signature for the reference's call sites (rs_replay_app.cpp:251, rs_align_app.cpp:303).
 inline bool AlignRgbd(AlignContext& ctx, const DepthFrame& src, const DepthFrame& dst, const Eigen::Matrix3f& K,
                       const AlignParams& params, Eigen::Isometry3f* const transform, AlignStats* const stats = nullptr) {

@@ -347,6 +347,56 @@ int32_t rst_solve_kabsch(rst_ctx* ctx, const rst_cloud* src, const rst_cloud* ds
 int32_t rst_cloud_normals(rst_ctx* ctx, const rst_cloud* cloud, int32_t k, const float* viewpoint,
                           float grid_cell, float* normals_out);
 
+/* The cloud utilities of rs_tracker/common/point_cloud_utils.hpp:11-31 for callers that hold clouds (every caller of
+ * the reference does: rs_replay_app.cpp:229,246-247; rs_tracker.cpp:60-87). All pointers are HOST memory; every call
+ * builds the search grid of its cloud on the device (the KDTree3f argument of the reference has no counterpart) and
+ * then runs as many blocks as the cloud needs. grid_cell <= 0 picks the cell size automatically.
+ *
+ * FindCorrespondences(tree, source, &indices, &squared_distances)  point_cloud_utils.cpp:70-90: exact 1-NN of every
+ *   source point in `target`; ties go to the lowest index; a non-finite source point gets index -1, distance +inf. */
+int32_t rst_find_correspondences(rst_ctx* ctx, const rst_cloud* target, const rst_cloud* source, float grid_cell,
+                                 int32_t* indices_out, float* sq_dist_out);
+/* ComputeCovariances(tree, cloud, &covs, use_gicp)  point_cloud_utils.cpp:100-161: 32 nearest OTHER points, fp32
+ *   centroid + scatter; use_gicp = 0: / 31; use_gicp != 0: singular values replaced by (1, 1, 1e-2) (:139-154).
+ *   covs_out: n x 9 floats (row-major symmetric 3x3). */
+int32_t rst_cloud_covariances(rst_ctx* ctx, const rst_cloud* cloud, int32_t use_gicp, float grid_cell, float* covs_out);
+/* DownsampleVoxel(cloud_in, voxel_size, &cloud_out)  point_cloud_utils.cpp:34-68: key floor(p / voxel_size), the first
+ *   point of a voxel wins; output in first-occurrence order (the reference's order is unordered_map iteration order).
+ *   xyz_out must hold cloud_in->n points; *n_out = points kept. */
+int32_t rst_downsample_voxel(rst_ctx* ctx, const rst_cloud* cloud_in, float voxel_size, float* xyz_out, int32_t* n_out);
+/* RemoveNans(cloud_in, &cloud_out)  point_cloud_utils.cpp:163-174: keeps the points whose three coordinates are finite,
+ *   in order. xyz_out must hold cloud_in->n points. */
+int32_t rst_remove_nans(rst_ctx* ctx, const rst_cloud* cloud_in, float* xyz_out, int32_t* n_out);
+
+/* GICP plane-to-plane (rs_tracker/align: gicp_cost.hpp:40-73, align_gicp.cpp:41-163) on the device.
+ * Residual of correspondence i -> j = dst_indices[i]:  e = C^{-1/2} (R s_i + t - d_j),  C = C_d[j] + R C_s[i] R^T,
+ * robustified with ceres::HuberLoss(huber_delta) (the reference uses 0.5, align_gicp.cpp:67; <= 0 = no loss).
+ * cost = 1/2 sum rho(|e|^2) (ceres' final_cost, :113); A, b = Gauss-Newton normal equations sum w J^T J, sum w J^T e
+ * with J = C^{-1/2} [ -[p']x | I ], omega first (same convention as rst_stats), C held at the current rotation. */
+typedef struct rst_gicp_stats {
+  double cost;
+  double A[21];
+  double b[6];
+  int32_t count;     /* correspondences evaluated (dst index in range, finite residual) */
+  int32_t reserved;
+} rst_gicp_stats;
+
+/* The cost of the 7-argument ComputeAlignment (align_gicp.cpp:41-117) at `pose` (16 floats, column-major, src->dst) for
+ * GIVEN covariances (n x 9 / m x 9 floats, row-major) and correspondences (n entries, < 0 = none).
+ * residuals_out: n x 3 (nullable; rows without a correspondence are left untouched). HOST pointers. */
+int32_t rst_gicp_evaluate(rst_ctx* ctx, const rst_cloud* src, const rst_cloud* dst, const float* src_covs, const float* dst_covs,
+                          const int32_t* dst_indices, const float* pose, float huber_delta, float* residuals_out,
+                          rst_gicp_stats* stats_out);
+
+/* The 3-argument ComputeAlignment (align_gicp.cpp:119-163): covariances of both clouds (ComputeCovariances;
+ * use_gicp_covariances = 0 is what the reference passes), then `max_outer` (reference: 16) rounds of
+ * { FindCorrespondences(dst, pose * src); minimise the robustified cost over the fixed correspondences }. The reference
+ * minimises with Ceres (absent, out of scope): here `inner_iters` Levenberg-Marquardt steps on the normal equations
+ * above. pose_inout: initial guess in (the reference always starts from the identity, :147), result out. */
+int32_t rst_gicp_align(rst_ctx* ctx, const rst_cloud* src, const rst_cloud* dst, int32_t max_outer, int32_t inner_iters,
+                       float huber_delta, int32_t use_gicp_covariances, float grid_cell, float* pose_inout,
+                       rst_gicp_stats* stats_out);
+
 /* The reference caller's whole per-pair sequence on the device, from depth frames
  * (rs_replay_app.cpp:229,246-251): back-projection with invalid pixels at the origin
  * (rs_driver.cpp:83-88,201-202) -> RemoveNans -> DownsampleVoxel(voxel) (first point per voxel, in

@@ -396,6 +396,15 @@ def ref_find_correspondences(dst, src):
     return idx, d2
 
 
+def ref_covariances(pts, use_gicp=False):
+    """ComputeCovariances (point_cloud_utils.cpp:100-161) through the compiled reference: [n,3,3] float32."""
+    p = _f32(pts)
+    out = np.empty((len(p), 3, 3), dtype=np.float32)
+    ref_lib().ref_covariances(p.ctypes.data_as(C.c_void_p), C.c_int32(len(p)), C.c_int32(1 if use_gicp else 0),
+                              out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def ref_normals(pts, k=16, viewpoint=(0.0, 0.0, 0.0)):
     p = _f32(pts)
     vp = _f32(viewpoint)
@@ -418,3 +427,61 @@ def ref_align_depth_pairs(src, dst, intr, depth_scale=0.001, voxel=0.05, max_ite
                                     C.c_float(depth_scale), C.c_float(voxel), C.c_int32(max_iter), C.c_int32(n_threads),
                                     T.ctypes.data_as(C.c_void_p), ok.ctypes.data_as(C.c_void_p))
     return ok.astype(bool), np.stack([cm_to_pose(t) for t in T])
+
+
+# ---------------------------------------------------------------------------------------------
+# GICP plane-to-plane residual: float64 numpy restatement (TEST INFRASTRUCTURE, like everything in oracle/).
+#   gicp_cost.hpp:48-70   delta = R*src + t - dst;  cov = dst_cov + R*src_cov*R^T;  rsqrt_cov = V diag(eig^-1/2) V^T;
+#                         residual = rsqrt_cov * delta
+#   align_gicp.cpp:59-77  one residual block per correspondence (src i -> dst dst_indices[i]), ceres::HuberLoss(0.5)
+#   align_gicp.cpp:113    returns summary.final_cost = 1/2 * sum rho(|residual|^2)
+# The reference differentiates through rsqrt_cov with ceres autodiff; the Gauss-Newton normal equations returned here
+# hold the combined covariance at the current rotation (J = rsqrt_cov [ -[p']x | I ], left perturbation, omega first).
+# ---------------------------------------------------------------------------------------------
+def gicp_evaluate(src, dst, src_covs, dst_covs, dst_indices, T, huber=0.5):
+    s = np.asarray(src, dtype=np.float64); d = np.asarray(dst, dtype=np.float64)
+    Cs = np.asarray(src_covs, dtype=np.float64).reshape(-1, 3, 3); Cd = np.asarray(dst_covs, dtype=np.float64).reshape(-1, 3, 3)
+    idx = np.asarray(dst_indices)
+    T = np.asarray(T, dtype=np.float64)
+    R, t = T[:3, :3], T[:3, 3]
+    use = (idx >= 0) & (idx < len(d))
+    p = s @ R.T + t
+    e = np.zeros((len(s), 3))
+    delta = p[use] - d[idx[use]]
+    C = Cd[idx[use]] + R @ Cs[use] @ R.T
+    C = 0.5 * (C + np.swapaxes(C, 1, 2))
+    lam, V = np.linalg.eigh(C)
+    W = np.einsum("nik,nk,njk->nij", V, 1.0 / np.sqrt(lam), V)
+    ee = np.einsum("nij,nj->ni", W, delta)
+    e[use] = ee
+    sq = (ee * ee).sum(1)
+    if huber > 0:
+        out = sq > huber * huber
+        w = np.where(out, huber / np.sqrt(np.maximum(sq, 1e-300)), 1.0)
+        rho = np.where(out, 2.0 * huber * np.sqrt(sq) - huber * huber, sq)
+    else:
+        w, rho = np.ones_like(sq), sq
+    pp = p[use]
+    negpx = np.zeros((len(pp), 3, 3))
+    negpx[:, 0, 1], negpx[:, 0, 2] = pp[:, 2], -pp[:, 1]
+    negpx[:, 1, 0], negpx[:, 1, 2] = -pp[:, 2], pp[:, 0]
+    negpx[:, 2, 0], negpx[:, 2, 1] = pp[:, 1], -pp[:, 0]
+    J = np.concatenate([W @ negpx, W], axis=2)                      # n x 3 x 6
+    A = np.einsum("n,nki,nkj->ij", w, J, J)
+    b = np.einsum("n,nki,nk->i", w, J, ee)
+    return dict(residuals=e, cost=0.5 * rho.sum(), A=A[np.triu_indices(6)], b=b, count=int(use.sum()), J=J, w=w)
+
+
+def covariances(pts, use_gicp=False, k=32):
+    """ComputeCovariances (point_cloud_utils.cpp:100-161), float64 numpy restatement over scipy's exact k-NN."""
+    from scipy.spatial import cKDTree
+    p = np.asarray(pts, dtype=np.float64)
+    _, idx = cKDTree(p).query(p, k=k + 1)
+    nb = p[idx[:, 1:]]
+    dl = nb - nb.mean(1, keepdims=True)
+    C = np.einsum("nki,nkj->nij", dl, dl)
+    if not use_gicp:
+        return C / (k - 1)
+    lam, V = np.linalg.eigh(C)                                       # ascending: column 0 = plane normal
+    v = np.array([1e-2, 1.0, 1.0])
+    return np.einsum("nik,k,njk->nij", V, v, V)

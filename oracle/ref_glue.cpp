@@ -90,6 +90,16 @@ void ref_align_depth_pairs(const unsigned short* src_depth, const unsigned short
   }
 }
 
+void ref_covariances(const float* pts, int n, int use_gicp, float* out) {
+  Cloud3f s; to_cloud(pts, n, &s);
+  const rs_tracker::KDTree3f tree{std::cref(s), 10};
+  std::vector<Eigen::Matrix3f> covs;
+  rs_tracker::ComputeCovariances(tree, s, &covs, use_gicp != 0);
+  for (int i = 0; i < n; ++i)
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) out[9 * i + 3 * r + c] = covs[i](r, c);
+}
+
 void ref_normals(const float* pts, int n, int k, const float* viewpoint, float* out) {
   Cloud3f s, nrm; to_cloud(pts, n, &s);
   const rs_tracker::KDTree3f tree{std::cref(s), 10};

@@ -49,6 +49,10 @@ class Stats(C.Structure):
                 ("any_status", C.c_int32), ("failed_iterations", C.c_int32), ("sum_wr2", C.c_double), ("A", C.c_double * 21), ("b", C.c_double * 6)]
 
 
+class GicpStats(C.Structure):
+    _fields_ = [("cost", C.c_double), ("A", C.c_double * 21), ("b", C.c_double * 6), ("count", C.c_int32), ("reserved", C.c_int32)]
+
+
 class Cloud(C.Structure):
     _fields_ = [("xyz", C.c_void_p), ("n", C.c_int32)]
 
@@ -73,6 +77,8 @@ ALIGN_SYMBOLS = [
     "rst_level_info", "rst_read_depth", "rst_read_geometry", "rst_read_intensity", "rst_evaluate", "rst_launch_count",
     "rst_copy_results_device", "rst_profile_enable", "rst_profile_read", "rst_set_pipeline_chunk", "rst_set_stream_split", "rst_align_pairs_async", "rst_align_sequence_async", "rst_wait", "rst_icp3d_pairs", "rst_solve_kabsch", "rst_cloud_normals", "rst_icp3d_depth", "rst_icp3d_read_cloud",
     "rst_set_schedule", "rst_set_cluster_size", "rst_max_active_clusters",
+    "rst_find_correspondences", "rst_cloud_covariances", "rst_downsample_voxel", "rst_remove_nans",
+    "rst_gicp_evaluate", "rst_gicp_align",
 ]
 
 _align = None
@@ -129,6 +135,20 @@ def align_lib() -> C.CDLL:
         lib.rst_icp3d_depth.argtypes = [C.c_void_p, P(Frame), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, P(Intrinsics),
                                         C.c_float, C.c_float, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.rst_icp3d_depth.restype = C.c_int32
+        lib.rst_find_correspondences.argtypes = [C.c_void_p, P(Cloud), P(Cloud), C.c_float, C.c_void_p, C.c_void_p]
+        lib.rst_find_correspondences.restype = C.c_int32
+        lib.rst_cloud_covariances.argtypes = [C.c_void_p, P(Cloud), C.c_int32, C.c_float, C.c_void_p]
+        lib.rst_cloud_covariances.restype = C.c_int32
+        lib.rst_downsample_voxel.argtypes = [C.c_void_p, P(Cloud), C.c_float, C.c_void_p, P(C.c_int32)]
+        lib.rst_downsample_voxel.restype = C.c_int32
+        lib.rst_remove_nans.argtypes = [C.c_void_p, P(Cloud), C.c_void_p, P(C.c_int32)]
+        lib.rst_remove_nans.restype = C.c_int32
+        lib.rst_gicp_evaluate.argtypes = [C.c_void_p, P(Cloud), P(Cloud), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
+                                          C.c_void_p, P(GicpStats)]
+        lib.rst_gicp_evaluate.restype = C.c_int32
+        lib.rst_gicp_align.argtypes = [C.c_void_p, P(Cloud), P(Cloud), C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_float,
+                                       C.c_void_p, P(GicpStats)]
+        lib.rst_gicp_align.restype = C.c_int32
         lib.rst_icp3d_read_cloud.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
         lib.rst_icp3d_read_cloud.restype = C.c_int32
         lib.rst_begin.argtypes = [C.c_void_p, C.c_int32, C.c_int32, P(Intrinsics), P(Params)]

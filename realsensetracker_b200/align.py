@@ -182,6 +182,62 @@ class Aligner:
         self._check(self._lib.rst_cloud_normals(self._ctx, C.byref(cs), k, vp.ctypes.data, grid_cell, out.ctypes.data))
         return out
 
+    def find_correspondences(self, target, source, grid_cell: float = 0.0):
+        """FindCorrespondences(tree(target), source, &indices, &squared_distances) (point_cloud_utils.cpp:70-90) on the GPU."""
+        T_, S = np.ascontiguousarray(target, dtype=np.float32), np.ascontiguousarray(source, dtype=np.float32)
+        idx = np.empty(len(S), dtype=np.int32); d2 = np.empty(len(S), dtype=np.float32)
+        ct, cs = N.Cloud(T_.ctypes.data, len(T_)), N.Cloud(S.ctypes.data, len(S))
+        self._check(self._lib.rst_find_correspondences(self._ctx, C.byref(ct), C.byref(cs), grid_cell, idx.ctypes.data, d2.ctypes.data))
+        return idx, d2
+
+    def cloud_covariances(self, cloud, use_gicp: bool = False, grid_cell: float = 0.0) -> np.ndarray:
+        """ComputeCovariances(tree, cloud, &covs, use_gicp) (point_cloud_utils.cpp:100-161) on the GPU: [n,3,3] float32."""
+        S = np.ascontiguousarray(cloud, dtype=np.float32)
+        out = np.empty((len(S), 3, 3), dtype=np.float32)
+        cs = N.Cloud(S.ctypes.data, len(S))
+        self._check(self._lib.rst_cloud_covariances(self._ctx, C.byref(cs), 1 if use_gicp else 0, grid_cell, out.ctypes.data))
+        return out
+
+    def downsample_voxel(self, cloud, voxel: float) -> np.ndarray:
+        """DownsampleVoxel (point_cloud_utils.cpp:34-68) on the GPU; first point per voxel, first-occurrence order."""
+        S = np.ascontiguousarray(cloud, dtype=np.float32)
+        out = np.empty_like(S); n = C.c_int32(0)
+        cs = N.Cloud(S.ctypes.data, len(S))
+        self._check(self._lib.rst_downsample_voxel(self._ctx, C.byref(cs), voxel, out.ctypes.data, C.byref(n)))
+        return out[:n.value].copy()
+
+    def remove_nans(self, cloud) -> np.ndarray:
+        """RemoveNans (point_cloud_utils.cpp:163-174) on the GPU."""
+        S = np.ascontiguousarray(cloud, dtype=np.float32)
+        out = np.empty_like(S); n = C.c_int32(0)
+        cs = N.Cloud(S.ctypes.data, len(S))
+        self._check(self._lib.rst_remove_nans(self._ctx, C.byref(cs), out.ctypes.data, C.byref(n)))
+        return out[:n.value].copy()
+
+    def gicp_evaluate(self, src, dst, src_covs, dst_covs, dst_indices, T, huber: float = 0.5, want_residuals: bool = True):
+        """GICP residuals / cost / normal equations at pose T (gicp_cost.hpp:40-73, align_gicp.cpp:59-77) on the GPU."""
+        S, D = np.ascontiguousarray(src, dtype=np.float32), np.ascontiguousarray(dst, dtype=np.float32)
+        cs_, cd_ = np.ascontiguousarray(src_covs, dtype=np.float32), np.ascontiguousarray(dst_covs, dtype=np.float32)
+        idx = np.ascontiguousarray(dst_indices, dtype=np.int32)
+        pose = pose_to_cm(T)
+        res = np.zeros((len(S), 3), dtype=np.float32) if want_residuals else None
+        st = N.GicpStats()
+        a, b = N.Cloud(S.ctypes.data, len(S)), N.Cloud(D.ctypes.data, len(D))
+        self._check(self._lib.rst_gicp_evaluate(self._ctx, C.byref(a), C.byref(b), cs_.ctypes.data, cd_.ctypes.data, idx.ctypes.data,
+                                                pose.ctypes.data, huber, res.ctypes.data if res is not None else None, C.byref(st)))
+        return res, st
+
+    def gicp_align(self, src, dst, max_outer: int = 16, inner_iters: int = 4, huber: float = 0.5, use_gicp_covariances: bool = False,
+                   T0=None, grid_cell: float = 0.0):
+        """The 3-argument ComputeAlignment (align_gicp.cpp:119-163) on the GPU. Returns (pose 4x4, GicpStats)."""
+        S, D = np.ascontiguousarray(src, dtype=np.float32), np.ascontiguousarray(dst, dtype=np.float32)
+        pose = pose_to_cm(np.eye(4) if T0 is None else T0).copy()
+        st = N.GicpStats()
+        a, b = N.Cloud(S.ctypes.data, len(S)), N.Cloud(D.ctypes.data, len(D))
+        self._check(self._lib.rst_gicp_align(self._ctx, C.byref(a), C.byref(b), max_outer, inner_iters, huber, 1 if use_gicp_covariances else 0,
+                                             grid_cell, pose.ctypes.data, C.byref(st)))
+        return cm_to_pose(pose), st
+
     def icp3d_depth(self, frames: np.ndarray, src_idx, dst_idx, intr, depth_scale: float = 0.001, voxel: float = 0.05,
                     max_iter: int = 128, T0=None, grid_cell: float = 0.1):
         """The reference caller's per-pair sequence from depth frames (rs_replay_app.cpp:229,246-251), on the GPU.

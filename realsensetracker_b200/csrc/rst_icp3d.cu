@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "rst_align.h"
+#include "rst_device.cuh"
 #include "rst_internal.h"
 
 namespace {
@@ -566,7 +567,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_kabsch(const float* __restrict_
 // n . (p - viewpoint) <= 0 (:210-214). One block per cloud: the grid of the cloud is built exactly as
 // for the ICP, then each thread owns points tid, tid + 1024, ...
 // ----------------------------------------------------------------------------------------------
-constexpr int kMaxK = 32;
+constexpr int kMaxK = 33;   // ComputeCovariances asks for 32 neighbours + the point itself
 
 struct NormalsDesc {
   const float* pts; int n;
@@ -668,6 +669,309 @@ __global__ void __launch_bounds__(kThreads, 1) k_normals(const NormalsDesc* __re
     const float sgn = ray > 0.f ? -1.f : 1.f;
     for (int a = 0; a < 3; ++a) P.normals[3 * i + a] = sgn * nv[a];
   }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Multi-block cloud utilities: the grid of a cloud is built once (one block, k_grid_build) and then
+// queried by as many blocks as the cloud needs, so a single cloud uses the whole GPU.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) k_grid_build(const float* __restrict__ pts, int n, float grid_cell, int* cell_start,
+                                                            int* cell_fill, float4* sorted, Grid* out) {
+  const Grid g = build_grid(pts, n, grid_cell, cell_start, cell_fill, sorted);
+  if (threadIdx.x == 0) *out = g;
+}
+
+// FindCorrespondences (point_cloud_utils.cpp:70-90): exact 1-NN of every query point in the gridded target cloud.
+// A non-finite query has no neighbour: index -1, squared distance +inf.
+__global__ void __launch_bounds__(128) k_nn_query(const Grid* __restrict__ gp, const int* __restrict__ cell_start,
+                                                  const float4* __restrict__ sorted, const float* __restrict__ q, int nq,
+                                                  int* __restrict__ idx, float* __restrict__ d2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const Grid g = *gp;
+  const float px = q[3 * i], py = q[3 * i + 1], pz = q[3 * i + 2];
+  int j = -1; float d = __int_as_float(0x7f800000);
+  if (isfinite(px) && isfinite(py) && isfinite(pz)) nn_search(g, cell_start, sorted, px, py, pz, &j, &d);
+  idx[i] = j; d2[i] = d;
+}
+
+// eigen-decomposition of a symmetric 3x3 (cyclic Jacobi, fp32): values descending, vectors in the columns of V
+__device__ void sym_eig3_desc(const float* C, float* val, float* V) {
+  float a[9], v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int i = 0; i < 9; ++i) a[i] = C[i];
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    float off = 0.f;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        off = fmaxf(off, fabsf(a[3 * p + q]));
+        if (fabsf(a[3 * p + q]) <= 1e-37f) continue;
+        const float theta = (a[3 * q + q] - a[3 * p + p]) / (2.f * a[3 * p + q]);
+        const float t = (theta >= 0 ? 1.f : -1.f) / (fabsf(theta) + sqrtf(1.f + theta * theta));
+        const float c = 1.f / sqrtf(1.f + t * t), s = c * t;
+        for (int k = 0; k < 3; ++k) { const float akp = a[3 * k + p], akq = a[3 * k + q]; a[3 * k + p] = c * akp - s * akq; a[3 * k + q] = s * akp + c * akq; }
+        for (int k = 0; k < 3; ++k) { const float apk = a[3 * p + k], aqk = a[3 * q + k]; a[3 * p + k] = c * apk - s * aqk; a[3 * q + k] = s * apk + c * aqk; }
+        for (int k = 0; k < 3; ++k) { const float vkp = v[3 * k + p], vkq = v[3 * k + q]; v[3 * k + p] = c * vkp - s * vkq; v[3 * k + q] = s * vkp + c * vkq; }
+      }
+    if (off < 1e-12f * (fabsf(a[0]) + fabsf(a[4]) + fabsf(a[8]))) break;
+  }
+  int o[3] = {0, 1, 2};
+  const float d[3] = {a[0], a[4], a[8]};
+  if (d[o[0]] < d[o[1]]) { const int t = o[0]; o[0] = o[1]; o[1] = t; }
+  if (d[o[1]] < d[o[2]]) { const int t = o[1]; o[1] = o[2]; o[2] = t; }
+  if (d[o[0]] < d[o[1]]) { const int t = o[0]; o[0] = o[1]; o[1] = t; }
+  for (int k = 0; k < 3; ++k) {
+    val[k] = d[o[k]];
+    for (int r = 0; r < 3; ++r) V[3 * r + k] = v[3 * r + o[k]];
+  }
+}
+
+// ComputeCovariances (point_cloud_utils.cpp:100-161): for every point the 32 nearest OTHER points (knnSearch of 33,
+// entry 0 = the point itself is skipped, :121-134), fp32 centroid and scatter matrix in ascending-distance order;
+// use_gicp = 0: divided by 31 (:157); use_gicp = 1: the scatter's singular vectors U recombined with singular values
+// (1, 1, 1e-2) (:139-154). covs_out: n x 9 floats, row-major 3x3 (the matrices are symmetric).
+__global__ void __launch_bounds__(128) k_covariances(const Grid* __restrict__ gp, const int* __restrict__ cell_start,
+                                                     const float4* __restrict__ sorted, const float* __restrict__ pts, int n,
+                                                     int use_gicp, float* __restrict__ covs) {
+  constexpr int kNb = 32;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Grid g = *gp;
+  float bd[kMaxK]; int bj[kMaxK];
+  knn_search(g, cell_start, sorted, pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], kNb + 1, bd, bj);
+  float cen[3] = {0.f, 0.f, 0.f};
+  for (int q = 1; q <= kNb; ++q) for (int a = 0; a < 3; ++a) cen[a] += pts[3 * bj[q] + a];
+  for (int a = 0; a < 3; ++a) cen[a] /= (float)kNb;
+  float C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int q = 1; q <= kNb; ++q) {
+    float d[3];
+    for (int a = 0; a < 3; ++a) d[a] = pts[3 * bj[q] + a] - cen[a];
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) C[3 * a + b] += d[a] * d[b];
+  }
+  if (use_gicp) {
+    float val[3], U[9];
+    sym_eig3_desc(C, val, U);
+    for (int e = 0; e < 9; ++e) C[e] = 0.f;
+    for (int k = 0; k < 3; ++k) {
+      const float v = k == 2 ? 1e-2f : 1.f;   // gicp_epsilon for the smallest singular value (:147-151)
+      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) C[3 * a + b] += v * U[3 * a + k] * U[3 * b + k];
+    }
+  } else {
+    for (int e = 0; e < 9; ++e) C[e] /= (float)(kNb - 1);
+  }
+  for (int e = 0; e < 9; ++e) covs[9 * (size_t)i + e] = C[e];
+}
+
+// DownsampleVoxel (point_cloud_utils.cpp:34-68) for a cloud: key = floor(p / voxel), the FIRST point of a voxel wins.
+// Pass 1 (any number of blocks): atomicMin(point index) per voxel in an open-addressing table.
+__global__ void __launch_bounds__(256) k_voxel_insert(const float* __restrict__ pts, int n, float voxel, unsigned long long* keys,
+                                                      int* vals, uint32_t cap_mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float p[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+  const unsigned long long key = voxel_key(p, voxel);
+  uint32_t slot = hash_key(key) & cap_mask;
+  for (;;) {
+    const unsigned long long prev = atomicCAS(keys + slot, kEmptyKey, key);
+    if (prev == kEmptyKey || prev == key) { atomicMin(vals + slot, i); break; }
+    slot = (slot + 1) & cap_mask;
+  }
+}
+
+// Pass 2 (one block): order-preserving compaction of the points a predicate keeps. MODE 0: voxel winners
+// (first-occurrence order — the reference's order is unordered_map iteration order, implementation-defined);
+// MODE 1: RemoveNans (point_cloud_utils.cpp:163-174), all three coordinates finite.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) k_compact_points(const float* __restrict__ pts, int n, float voxel,
+                                                                const unsigned long long* __restrict__ keys, const int* __restrict__ vals,
+                                                                uint32_t cap_mask, float* __restrict__ out, int* __restrict__ count) {
+  __shared__ int s_scan[kWarps];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (n + kThreads - 1) / kThreads;
+  const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
+  auto keep = [&](int i) -> bool {
+    const float p[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+    if (MODE == 1) return isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]);
+    const unsigned long long key = voxel_key(p, voxel);
+    uint32_t slot = hash_key(key) & cap_mask;
+    while (keys[slot] != key) slot = (slot + 1) & cap_mask;
+    return vals[slot] == i;
+  };
+  int local = 0;
+  for (int i = i0; i < i1; ++i) local += keep(i) ? 1 : 0;
+  int incl = local;
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) s_scan[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = s_scan[lane];
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+    s_scan[lane] = v;
+  }
+  __syncthreads();
+  int pos = incl - local + (warp > 0 ? s_scan[warp - 1] : 0);
+  for (int i = i0; i < i1; ++i)
+    if (keep(i)) { out[3 * pos] = pts[3 * i]; out[3 * pos + 1] = pts[3 * i + 1]; out[3 * pos + 2] = pts[3 * i + 2]; ++pos; }
+  if (tid == kThreads - 1) *count = pos;
+}
+
+// ----------------------------------------------------------------------------------------------
+// GICP plane-to-plane residual (gicp_cost.hpp:40-73) + ceres::HuberLoss(0.5) (align_gicp.cpp:67), one thread per
+// correspondence:  e = C^{-1/2} (R s + t - d),  C = C_d + R C_s R^T,  C^{-1/2} = V diag(lambda^{-1/2}) V^T from the
+// eigen-decomposition of the symmetric C (the reference calls the general EigenSolver only because the self-adjoint
+// one does not compile with ceres::Jet, :58-62).  Gauss-Newton linearisation with C held at the current rotation:
+// J = C^{-1/2} [ -[p']x | I ] (left perturbation, p' = R s + t), robust weight w = rho'(|e|^2).  Accumulates
+// cost = 1/2 sum rho(|e|^2) (ceres' final_cost convention, :113), A = sum w J^T J (21), b = sum w J^T e (6), count:
+// 29 sums, fp64, block partials in block order (deterministic), summed by k_gicp_finish.
+// ----------------------------------------------------------------------------------------------
+constexpr int kGicpThreads = 128;
+constexpr int kGicpSums = 29;   // A(21) b(6) cost count
+
+__global__ void __launch_bounds__(kGicpThreads) k_gicp_residuals(const float* __restrict__ src, const float* __restrict__ dst,
+                                                                 const float* __restrict__ src_cov, const float* __restrict__ dst_cov,
+                                                                 const int* __restrict__ dst_idx, int n, int m, const float* __restrict__ pose_cm,
+                                                                 float huber, float* __restrict__ resid, double* __restrict__ partials) {
+  __shared__ double s_part[kGicpThreads / 32][kGicpSums];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i = blockIdx.x * kGicpThreads + tid;
+  double acc[kGicpSums];
+#pragma unroll
+  for (int k = 0; k < kGicpSums; ++k) acc[k] = 0.0;
+  const int j = i < n ? dst_idx[i] : -1;
+  if (i < n && j >= 0 && j < m) {
+    float R[9], t[3];
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) R[3 * r + c] = pose_cm[r + 4 * c]; t[r] = pose_cm[12 + r]; }
+    float p[3], delta[3];
+    for (int r = 0; r < 3; ++r) {
+      p[r] = R[3 * r] * src[3 * i] + R[3 * r + 1] * src[3 * i + 1] + R[3 * r + 2] * src[3 * i + 2] + t[r];
+      delta[r] = p[r] - dst[3 * j + r];
+    }
+    float RC[9], C[9];
+    const float* Cs = src_cov + 9 * (size_t)i;
+    const float* Cd = dst_cov + 9 * (size_t)j;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) RC[3 * r + c] = R[3 * r] * Cs[c] + R[3 * r + 1] * Cs[3 + c] + R[3 * r + 2] * Cs[6 + c];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) C[3 * r + c] = Cd[3 * r + c] + (RC[3 * r] * R[3 * c] + RC[3 * r + 1] * R[3 * c + 1] + RC[3 * r + 2] * R[3 * c + 2]);
+    for (int r = 0; r < 3; ++r)   // symmetrise: the Jacobi sweep reads both triangles
+      for (int c = r + 1; c < 3; ++c) { const float v = 0.5f * (C[3 * r + c] + C[3 * c + r]); C[3 * r + c] = C[3 * c + r] = v; }
+    float val[3], V[9], W[9];
+    sym_eig3_desc(C, val, V);
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        float a = 0.f;
+        for (int k = 0; k < 3; ++k) a += V[3 * r + k] * rsqrtf(val[k]) * V[3 * c + k];
+        W[3 * r + c] = a;   // C^{-1/2}
+      }
+    float e[3];
+    for (int r = 0; r < 3; ++r) e[r] = W[3 * r] * delta[0] + W[3 * r + 1] * delta[1] + W[3 * r + 2] * delta[2];
+    if (resid) { resid[3 * i] = e[0]; resid[3 * i + 1] = e[1]; resid[3 * i + 2] = e[2]; }
+    const float s = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+    float w = 1.f, rho = s;
+    if (huber > 0.f && s > huber * huber) { const float rt = sqrtf(s); w = huber / rt; rho = 2.f * huber * rt - huber * huber; }
+    if (isfinite(s)) {
+      // J = W [ -[p']x | I ]: columns 0..2 = W * (-[p']x), columns 3..5 = W
+      float J[3][6];
+      for (int r = 0; r < 3; ++r) {
+        J[r][0] = W[3 * r + 2] * p[1] - W[3 * r + 1] * p[2];    // -[p']x = [[0, p2, -p1], [-p2, 0, p0], [p1, -p0, 0]]
+        J[r][1] = W[3 * r] * p[2] - W[3 * r + 2] * p[0];
+        J[r][2] = W[3 * r + 1] * p[0] - W[3 * r] * p[1];
+        J[r][3] = W[3 * r]; J[r][4] = W[3 * r + 1]; J[r][5] = W[3 * r + 2];
+      }
+      int k = 0;
+      for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b) {
+          acc[k++] = (double)(w * (J[0][a] * J[0][b] + J[1][a] * J[1][b] + J[2][a] * J[2][b]));
+        }
+      for (int a = 0; a < 6; ++a) acc[21 + a] = (double)(w * (J[0][a] * e[0] + J[1][a] * e[1] + J[2][a] * e[2]));
+      acc[27] = 0.5 * (double)rho;
+      acc[28] = 1.0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kGicpSums; ++k) {
+    double x = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) s_part[warp][k] = x;
+  }
+  __syncthreads();
+  if (tid < kGicpSums) {
+    double x = 0.0;
+    for (int w2 = 0; w2 < kGicpThreads / 32; ++w2) x += s_part[w2][tid];
+    partials[(size_t)blockIdx.x * kGicpSums + tid] = x;
+  }
+}
+
+__global__ void k_transform_points(const float* __restrict__ in, int n, const float* __restrict__ pose_cm, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = in[3 * i], y = in[3 * i + 1], z = in[3 * i + 2];
+  for (int r = 0; r < 3; ++r) out[3 * i + r] = pose_cm[r] * x + pose_cm[4 + r] * y + pose_cm[8 + r] * z + pose_cm[12 + r];
+}
+
+struct GicpState {
+  double sums[kGicpSums];       // of the last evaluation (at Rt)
+  double good_sums[kGicpSums];  // of the last ACCEPTED pose (at good_Rt)
+  double Rt[12];                // fp64 pose the last evaluation ran at: row-major R then t
+  double good_Rt[12];
+  float pose_cm[16];            // fp32 copy of Rt, what the kernels read
+  double lambda;                // Levenberg-Marquardt damping
+  int have_good, accepted, rejected;
+};
+
+__device__ void gicp_set_pose(GicpState* st, const double* Rt) {
+  for (int k = 0; k < 12; ++k) st->Rt[k] = Rt[k];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) st->pose_cm[r + 4 * c] = (float)Rt[3 * r + c];
+    st->pose_cm[12 + r] = (float)Rt[9 + r];
+    st->pose_cm[4 * r + 3] = 0.f;
+  }
+  st->pose_cm[15] = 1.f;
+}
+
+// One warp: sums the block partials in block order, then (lane 0)
+//   mode 0: evaluation only;
+//   mode 1: Levenberg-Marquardt bookkeeping + step: the pose just evaluated is accepted when it did not raise the
+//           cost of the last accepted pose (lambda / 3), else rejected (back to the accepted pose, lambda * 10);
+//           the next trial pose is Exp(xi) * accepted pose with (A + lambda diag A) xi = -b;
+//   mode 2: as 1 after new correspondences (costs are not comparable: the evaluated pose is accepted as is);
+//   mode 3: final check: a trial pose that raised the cost is dropped, sums = those of the accepted pose.
+__global__ void __launch_bounds__(32) k_gicp_finish(const double* __restrict__ partials, int n_blocks, GicpState* st, int mode) {
+  const int lane = threadIdx.x;
+  double s = 0.0;
+  if (lane < kGicpSums) for (int b = 0; b < n_blocks; ++b) s += partials[(size_t)b * kGicpSums + lane];
+  if (lane < kGicpSums) st->sums[lane] = s;
+  __syncwarp();
+  if (lane != 0 || mode == 0) return;
+  const bool worse = mode != 2 && st->have_good && !(st->sums[27] <= st->good_sums[27]);
+  if (worse) {
+    st->lambda = fmin(st->lambda * 10.0, 1e6);
+    st->rejected += 1;
+  } else {
+    for (int k = 0; k < kGicpSums; ++k) st->good_sums[k] = st->sums[k];
+    for (int k = 0; k < 12; ++k) st->good_Rt[k] = st->Rt[k];
+    if (st->have_good && mode != 2) st->lambda = fmax(st->lambda / 3.0, 1e-9);
+    st->have_good = 1;
+    st->accepted += 1;
+  }
+  if (mode == 3) {
+    if (worse) { gicp_set_pose(st, st->good_Rt); for (int k = 0; k < kGicpSums; ++k) st->sums[k] = st->good_sums[k]; }
+    return;
+  }
+  double A[21], b[6], xi[6];
+  for (int k = 0; k < 21; ++k) A[k] = st->good_sums[k];
+  for (int k = 0; k < 6; ++k) b[k] = st->good_sums[21 + k];
+  const int dg[6] = {0, 6, 11, 15, 18, 20};
+  for (int k = 0; k < 6; ++k) A[dg[k]] *= (1.0 + st->lambda);
+  double Rn[12];
+  for (int k = 0; k < 12; ++k) Rn[k] = st->good_Rt[k];
+  if (rst::solve6(A, b, (int)st->good_sums[28], 6, 0.0, xi) == RST_STATUS_OK) {
+    rst::se3_update(xi, Rn);
+    bool fin = true;
+    for (int k = 0; k < 12; ++k) fin &= isfinite(Rn[k]);
+    if (!fin) for (int k = 0; k < 12; ++k) Rn[k] = st->good_Rt[k];
+  }
+  gicp_set_pose(st, Rn);
 }
 
 /* grow-only device/pinned arenas of the cloud engine, owned by the context */
@@ -996,7 +1300,7 @@ extern "C" int32_t rst_cloud_normals(rst_ctx* c, const rst_cloud* cloud, int32_t
   if (!c) return RST_ERR_INVALID_ARG;
   auto fail = [&](int code, const std::string& m) { rst::ctx_set_error(c, m); return code; };
   if (!cloud || !viewpoint || !normals_out || cloud->n < 0 || (cloud->n > 0 && !cloud->xyz)) return fail(RST_ERR_INVALID_ARG, "null argument");
-  if (k < 2 || k > kMaxK) return fail(RST_ERR_INVALID_ARG, "k must be in [2, 32]");
+  if (k < 2 || k > 32) return fail(RST_ERR_INVALID_ARG, "k must be in [2, 32]");
   if (cloud->n == 0) return RST_OK;
 #define ICP_CUDA(expr)                                                                   \
   do {                                                                                   \
@@ -1049,5 +1353,317 @@ extern "C" int32_t rst_cloud_normals(rst_ctx* c, const rst_cloud* cloud, int32_t
   ICP_CUDA(cudaStreamSynchronize(stream));
   std::memcpy(normals_out, H + o_nrm, sizeof(float) * 3 * n);
 #undef ICP_CUDA
+  return RST_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cloud utilities of rs_tracker/common (point_cloud_utils.hpp) for callers that hold clouds — which is every
+// caller of the reference (rs_replay_app.cpp:229,246-247; rs_tracker.cpp:60-87). HOST pointers in and out.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// one call's view of the context's grow-only arenas: offsets are taken first, then `commit` sizes the arenas
+struct CloudCall {
+  rst_ctx* c;
+  Icp3dState* st = nullptr;
+  cudaStream_t stream = nullptr;
+  size_t off = 0;
+  char* H = nullptr;
+  char* D = nullptr;
+  explicit CloudCall(rst_ctx* ctx) : c(ctx) {}
+  size_t take(size_t bytes) { const size_t o = off; off = align_up(off + bytes); return o; }
+  int fail(int code, const std::string& m) { rst::ctx_set_error(c, m); return code; }
+  int cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return RST_OK;
+    return fail(RST_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  }
+  int begin() {
+    int rc = cuda(cudaSetDevice(rst::ctx_device(c)), "cudaSetDevice");
+    if (rc != RST_OK) return rc;
+    stream = rst::ctx_stream(c);
+    void (**free_fn)(void*) = nullptr;
+    void** slot = rst::ctx_ext_slot(c, &free_fn);
+    if (!*slot) { *slot = new Icp3dState(); *free_fn = icp3d_free; }
+    st = static_cast<Icp3dState*>(*slot);
+    st->last_frames = 0;
+    return RST_OK;
+  }
+  int commit(size_t host_bytes) {   // device arena >= off, pinned arena >= host_bytes
+    int rc;
+    if (st->d_bytes < off) {
+      if ((rc = cuda(cudaStreamSynchronize(stream), "sync")) != RST_OK) return rc;
+      cudaFree(st->d_arena); st->d_arena = nullptr; st->d_bytes = 0;
+      if ((rc = cuda(cudaMalloc(&st->d_arena, off), "cudaMalloc")) != RST_OK) return rc;
+      st->d_bytes = off;
+    }
+    if (st->h_bytes < host_bytes) {
+      if ((rc = cuda(cudaStreamSynchronize(stream), "sync")) != RST_OK) return rc;
+      cudaFreeHost(st->h_arena); st->h_arena = nullptr; st->h_bytes = 0;
+      if ((rc = cuda(cudaMallocHost(&st->h_arena, host_bytes), "cudaMallocHost")) != RST_OK) return rc;
+      st->h_bytes = host_bytes;
+    }
+    H = static_cast<char*>(st->h_arena);
+    D = static_cast<char*>(st->d_arena);
+    return RST_OK;
+  }
+};
+
+#define CLOUD_TRY(expr)                              \
+  do {                                               \
+    const int rc_ = (expr);                          \
+    if (rc_ != RST_OK) return rc_;                   \
+  } while (0)
+
+bool cloud_ok(const rst_cloud* cl) { return cl && cl->n >= 0 && (cl->n == 0 || cl->xyz); }
+
+}  // namespace
+
+/* void FindCorrespondences(tree, source, &indices, &squared_distances)  point_cloud_utils.cpp:70-90 */
+extern "C" int32_t rst_find_correspondences(rst_ctx* c, const rst_cloud* target, const rst_cloud* source, float grid_cell,
+                                            int32_t* indices_out, float* sq_dist_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  CloudCall k(c);
+  if (!cloud_ok(target) || !cloud_ok(source) || !indices_out || !sq_dist_out) return k.fail(RST_ERR_INVALID_ARG, "null argument / bad cloud");
+  if (source->n == 0) return RST_OK;
+  if (target->n == 0) return k.fail(RST_ERR_INVALID_ARG, "the target cloud is empty");
+  CLOUD_TRY(k.begin());
+  const size_t m = (size_t)target->n, n = (size_t)source->n;
+  const size_t o_tgt = k.take(12 * m), o_src = k.take(12 * n);
+  const size_t upload = k.off;
+  const size_t o_idx = k.take(4 * n), o_d2 = k.take(4 * n);
+  const size_t host_end = k.off;
+  const size_t o_grid = k.take(sizeof(Grid)), o_cs = k.take(sizeof(int) * (kCellCap + 1)), o_cf = k.take(sizeof(int) * kCellCap);
+  const size_t o_sorted = k.take(sizeof(float4) * m);
+  CLOUD_TRY(k.commit(host_end));
+  std::memcpy(k.H + o_tgt, target->xyz, 12 * m);
+  std::memcpy(k.H + o_src, source->xyz, 12 * n);
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.D, k.H, upload, cudaMemcpyHostToDevice, k.stream), "H2D"));
+  k_grid_build<<<1, kThreads, 0, k.stream>>>(reinterpret_cast<const float*>(k.D + o_tgt), (int)m, grid_cell, reinterpret_cast<int*>(k.D + o_cs),
+                                             reinterpret_cast<int*>(k.D + o_cf), reinterpret_cast<float4*>(k.D + o_sorted),
+                                             reinterpret_cast<Grid*>(k.D + o_grid));
+  k_nn_query<<<(unsigned)((n + 127) / 128), 128, 0, k.stream>>>(reinterpret_cast<const Grid*>(k.D + o_grid), reinterpret_cast<const int*>(k.D + o_cs),
+                                                                  reinterpret_cast<const float4*>(k.D + o_sorted),
+                                                                  reinterpret_cast<const float*>(k.D + o_src), (int)n,
+                                                                  reinterpret_cast<int*>(k.D + o_idx), reinterpret_cast<float*>(k.D + o_d2));
+  CLOUD_TRY(k.cuda(cudaGetLastError(), "launch"));
+  rst::ctx_count_launches(c, 2);
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.H + o_idx, k.D + o_idx, host_end - o_idx, cudaMemcpyDeviceToHost, k.stream), "D2H"));
+  CLOUD_TRY(k.cuda(cudaStreamSynchronize(k.stream), "sync"));
+  std::memcpy(indices_out, k.H + o_idx, 4 * n);
+  std::memcpy(sq_dist_out, k.H + o_d2, 4 * n);
+  return RST_OK;
+}
+
+/* void ComputeCovariances(tree, cloud, &covs, use_gicp)  point_cloud_utils.cpp:100-161 */
+extern "C" int32_t rst_cloud_covariances(rst_ctx* c, const rst_cloud* cloud, int32_t use_gicp, float grid_cell, float* covs_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  CloudCall k(c);
+  if (!cloud_ok(cloud) || !covs_out) return k.fail(RST_ERR_INVALID_ARG, "null argument / bad cloud");
+  if (cloud->n == 0) return RST_OK;
+  CLOUD_TRY(k.begin());
+  const size_t n = (size_t)cloud->n;
+  const size_t o_pts = k.take(12 * n);
+  const size_t upload = k.off;
+  const size_t o_cov = k.take(36 * n);
+  const size_t host_end = k.off;
+  const size_t o_grid = k.take(sizeof(Grid)), o_cs = k.take(sizeof(int) * (kCellCap + 1)), o_cf = k.take(sizeof(int) * kCellCap);
+  const size_t o_sorted = k.take(sizeof(float4) * n);
+  CLOUD_TRY(k.commit(host_end));
+  std::memcpy(k.H + o_pts, cloud->xyz, 12 * n);
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.D, k.H, upload, cudaMemcpyHostToDevice, k.stream), "H2D"));
+  const float* pts = reinterpret_cast<const float*>(k.D + o_pts);
+  k_grid_build<<<1, kThreads, 0, k.stream>>>(pts, (int)n, grid_cell, reinterpret_cast<int*>(k.D + o_cs), reinterpret_cast<int*>(k.D + o_cf),
+                                             reinterpret_cast<float4*>(k.D + o_sorted), reinterpret_cast<Grid*>(k.D + o_grid));
+  k_covariances<<<(unsigned)((n + 127) / 128), 128, 0, k.stream>>>(reinterpret_cast<const Grid*>(k.D + o_grid), reinterpret_cast<const int*>(k.D + o_cs),
+                                                                     reinterpret_cast<const float4*>(k.D + o_sorted), pts, (int)n, use_gicp ? 1 : 0,
+                                                                     reinterpret_cast<float*>(k.D + o_cov));
+  CLOUD_TRY(k.cuda(cudaGetLastError(), "launch"));
+  rst::ctx_count_launches(c, 2);
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.H + o_cov, k.D + o_cov, 36 * n, cudaMemcpyDeviceToHost, k.stream), "D2H"));
+  CLOUD_TRY(k.cuda(cudaStreamSynchronize(k.stream), "sync"));
+  std::memcpy(covs_out, k.H + o_cov, 36 * n);
+  return RST_OK;
+}
+
+static int32_t compact_cloud(rst_ctx* c, const rst_cloud* in, float voxel, bool by_voxel, float* xyz_out, int32_t* n_out) {
+  CloudCall k(c);
+  if (!cloud_ok(in) || !xyz_out || !n_out) return k.fail(RST_ERR_INVALID_ARG, "null argument / bad cloud");
+  if (by_voxel && !(voxel > 0.f)) return k.fail(RST_ERR_INVALID_ARG, "voxel_size must be positive");
+  *n_out = 0;
+  if (in->n == 0) return RST_OK;
+  CLOUD_TRY(k.begin());
+  const size_t n = (size_t)in->n;
+  uint32_t cap = 1;
+  while (cap < 2 * n) cap <<= 1;   // load factor <= 0.5 even if every point is its own voxel
+  const size_t o_pts = k.take(12 * n);
+  const size_t upload = k.off;
+  const size_t o_out = k.take(12 * n), o_cnt = k.take(4);
+  const size_t host_end = k.off;
+  const size_t o_keys = k.take(by_voxel ? (size_t)cap * 8 : 0), o_vals = k.take(by_voxel ? (size_t)cap * 4 : 0);
+  CLOUD_TRY(k.commit(host_end));
+  std::memcpy(k.H + o_pts, in->xyz, 12 * n);
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.D, k.H, upload, cudaMemcpyHostToDevice, k.stream), "H2D"));
+  const float* pts = reinterpret_cast<const float*>(k.D + o_pts);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(k.D + o_keys);
+  int* vals = reinterpret_cast<int*>(k.D + o_vals);
+  if (by_voxel) {
+    CLOUD_TRY(k.cuda(cudaMemsetAsync(keys, 0, (size_t)cap * 8, k.stream), "memset"));
+    CLOUD_TRY(k.cuda(cudaMemsetAsync(vals, 0x7f, (size_t)cap * 4, k.stream), "memset"));   // 0x7f7f7f7f > any point index
+    k_voxel_insert<<<(unsigned)((n + 255) / 256), 256, 0, k.stream>>>(pts, (int)n, voxel, keys, vals, cap - 1);
+    k_compact_points<0><<<1, kThreads, 0, k.stream>>>(pts, (int)n, voxel, keys, vals, cap - 1, reinterpret_cast<float*>(k.D + o_out),
+                                                       reinterpret_cast<int*>(k.D + o_cnt));
+    rst::ctx_count_launches(c, 2);
+  } else {
+    k_compact_points<1><<<1, kThreads, 0, k.stream>>>(pts, (int)n, 0.f, nullptr, nullptr, 0u, reinterpret_cast<float*>(k.D + o_out),
+                                                       reinterpret_cast<int*>(k.D + o_cnt));
+    rst::ctx_count_launches(c, 1);
+  }
+  CLOUD_TRY(k.cuda(cudaGetLastError(), "launch"));
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.H + o_out, k.D + o_out, host_end - o_out, cudaMemcpyDeviceToHost, k.stream), "D2H"));
+  CLOUD_TRY(k.cuda(cudaStreamSynchronize(k.stream), "sync"));
+  const int cnt = *reinterpret_cast<const int*>(k.H + o_cnt);
+  std::memcpy(xyz_out, k.H + o_out, 12 * (size_t)cnt);
+  *n_out = cnt;
+  return RST_OK;
+}
+
+/* void DownsampleVoxel(cloud_in, voxel_size, &cloud_out)  point_cloud_utils.cpp:34-68 */
+extern "C" int32_t rst_downsample_voxel(rst_ctx* c, const rst_cloud* cloud_in, float voxel_size, float* xyz_out, int32_t* n_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  return compact_cloud(c, cloud_in, voxel_size, true, xyz_out, n_out);
+}
+
+/* void RemoveNans(cloud_in, &cloud_out)  point_cloud_utils.cpp:163-174 */
+extern "C" int32_t rst_remove_nans(rst_ctx* c, const rst_cloud* cloud_in, float* xyz_out, int32_t* n_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  return compact_cloud(c, cloud_in, 0.f, false, xyz_out, n_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GICP (align_gicp.cpp:41-163): the residual / normal-equation evaluation for GIVEN correspondences and covariances
+// (the 7-argument ComputeAlignment's cost, :59-77), and the 3-argument driver (:119-163): sample covariances, then
+// kMaxIter rounds of { FindCorrespondences, minimise over the fixed correspondences }. The reference minimises with
+// Ceres (Levenberg-Marquardt, DENSE_QR, autodiff through C^{-1/2}); Ceres is absent and out of scope, so the inner
+// minimisation is Levenberg-Marquardt on the Gauss-Newton normal equations of the same robustified cost.
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t rst_gicp_evaluate(rst_ctx* c, const rst_cloud* src, const rst_cloud* dst, const float* src_covs, const float* dst_covs,
+                                     const int32_t* dst_indices, const float* pose, float huber_delta, float* residuals_out,
+                                     rst_gicp_stats* stats_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  CloudCall k(c);
+  if (!cloud_ok(src) || !cloud_ok(dst) || !src_covs || !dst_covs || !dst_indices || !pose || !stats_out)
+    return k.fail(RST_ERR_INVALID_ARG, "null argument / bad cloud");
+  std::memset(stats_out, 0, sizeof(*stats_out));
+  if (src->n == 0 || dst->n == 0) return RST_OK;
+  CLOUD_TRY(k.begin());
+  const size_t n = (size_t)src->n, m = (size_t)dst->n;
+  const int n_blocks = (int)((n + kGicpThreads - 1) / kGicpThreads);
+  const size_t o_src = k.take(12 * n), o_dst = k.take(12 * m), o_sc = k.take(36 * n), o_dc = k.take(36 * m), o_idx = k.take(4 * n);
+  const size_t o_state = k.take(sizeof(GicpState));
+  const size_t upload = k.off;
+  const size_t o_res = k.take(12 * n);
+  const size_t host_end = k.off;
+  const size_t o_part = k.take(sizeof(double) * kGicpSums * (size_t)n_blocks);
+  CLOUD_TRY(k.commit(host_end));
+  std::memcpy(k.H + o_src, src->xyz, 12 * n); std::memcpy(k.H + o_dst, dst->xyz, 12 * m);
+  std::memcpy(k.H + o_sc, src_covs, 36 * n); std::memcpy(k.H + o_dc, dst_covs, 36 * m);
+  std::memcpy(k.H + o_idx, dst_indices, 4 * n);
+  GicpState* hs = reinterpret_cast<GicpState*>(k.H + o_state);
+  std::memset(hs, 0, sizeof(*hs));
+  std::memcpy(hs->pose_cm, pose, 64);
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.D, k.H, upload, cudaMemcpyHostToDevice, k.stream), "H2D"));
+  GicpState* ds = reinterpret_cast<GicpState*>(k.D + o_state);
+  k_gicp_residuals<<<n_blocks, kGicpThreads, 0, k.stream>>>(
+      reinterpret_cast<const float*>(k.D + o_src), reinterpret_cast<const float*>(k.D + o_dst), reinterpret_cast<const float*>(k.D + o_sc),
+      reinterpret_cast<const float*>(k.D + o_dc), reinterpret_cast<const int*>(k.D + o_idx), (int)n, (int)m, ds->pose_cm, huber_delta,
+      residuals_out ? reinterpret_cast<float*>(k.D + o_res) : nullptr, reinterpret_cast<double*>(k.D + o_part));
+  k_gicp_finish<<<1, 32, 0, k.stream>>>(reinterpret_cast<const double*>(k.D + o_part), n_blocks, ds, 0);
+  CLOUD_TRY(k.cuda(cudaGetLastError(), "launch"));
+  rst::ctx_count_launches(c, 2);
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.H + o_state, k.D + o_state, sizeof(GicpState), cudaMemcpyDeviceToHost, k.stream), "D2H"));
+  if (residuals_out) CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.H + o_res, k.D + o_res, 12 * n, cudaMemcpyDeviceToHost, k.stream), "D2H"));
+  CLOUD_TRY(k.cuda(cudaStreamSynchronize(k.stream), "sync"));
+  for (int i = 0; i < 21; ++i) stats_out->A[i] = hs->sums[i];
+  for (int i = 0; i < 6; ++i) stats_out->b[i] = hs->sums[21 + i];
+  stats_out->cost = hs->sums[27];
+  stats_out->count = (int32_t)hs->sums[28];
+  if (residuals_out) std::memcpy(residuals_out, k.H + o_res, 12 * n);
+  return RST_OK;
+}
+
+extern "C" int32_t rst_gicp_align(rst_ctx* c, const rst_cloud* src, const rst_cloud* dst, int32_t max_outer, int32_t inner_iters,
+                                  float huber_delta, int32_t use_gicp_covariances, float grid_cell, float* pose_inout, rst_gicp_stats* stats_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  CloudCall k(c);
+  if (!cloud_ok(src) || !cloud_ok(dst) || !pose_inout || max_outer < 0 || inner_iters < 1)
+    return k.fail(RST_ERR_INVALID_ARG, "null argument / bad cloud / bad iteration counts");
+  if (stats_out) std::memset(stats_out, 0, sizeof(*stats_out));
+  if (src->n < 3 || dst->n < 3) return k.fail(RST_ERR_INVALID_ARG, "clouds need at least 3 points");
+  CLOUD_TRY(k.begin());
+  const size_t n = (size_t)src->n, m = (size_t)dst->n;
+  const int n_blocks = (int)((n + kGicpThreads - 1) / kGicpThreads);
+  const size_t o_src = k.take(12 * n), o_dst = k.take(12 * m), o_state = k.take(sizeof(GicpState));
+  const size_t upload = k.off;
+  const size_t host_end = k.off;
+  const size_t o_sc = k.take(36 * n), o_dc = k.take(36 * m), o_idx = k.take(4 * n), o_d2 = k.take(4 * n), o_tmp = k.take(12 * n);
+  const size_t o_part = k.take(sizeof(double) * kGicpSums * (size_t)n_blocks);
+  const size_t o_grid = k.take(sizeof(Grid)), o_cs = k.take(sizeof(int) * (kCellCap + 1)), o_cf = k.take(sizeof(int) * kCellCap);
+  const size_t o_sorted = k.take(sizeof(float4) * (n > m ? n : m));
+  CLOUD_TRY(k.commit(host_end));
+  std::memcpy(k.H + o_src, src->xyz, 12 * n); std::memcpy(k.H + o_dst, dst->xyz, 12 * m);
+  GicpState* hs = reinterpret_cast<GicpState*>(k.H + o_state);
+  std::memset(hs, 0, sizeof(*hs));
+  std::memcpy(hs->pose_cm, pose_inout, 64);
+  for (int r = 0; r < 3; ++r) { for (int cc = 0; cc < 3; ++cc) hs->Rt[3 * r + cc] = pose_inout[r + 4 * cc]; hs->Rt[9 + r] = pose_inout[12 + r]; }
+  hs->lambda = 1e-4;
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.D, k.H, upload, cudaMemcpyHostToDevice, k.stream), "H2D"));
+  const float* d_src = reinterpret_cast<const float*>(k.D + o_src);
+  const float* d_dst = reinterpret_cast<const float*>(k.D + o_dst);
+  Grid* d_grid = reinterpret_cast<Grid*>(k.D + o_grid);
+  int* d_cs = reinterpret_cast<int*>(k.D + o_cs); int* d_cf = reinterpret_cast<int*>(k.D + o_cf);
+  float4* d_sorted = reinterpret_cast<float4*>(k.D + o_sorted);
+  GicpState* ds = reinterpret_cast<GicpState*>(k.D + o_state);
+  int launches = 0;
+  // covariances of both clouds (align_gicp.cpp:136-140; the reference passes use_gicp = false)
+  k_grid_build<<<1, kThreads, 0, k.stream>>>(d_src, (int)n, grid_cell, d_cs, d_cf, d_sorted, d_grid);
+  k_covariances<<<(unsigned)((n + 127) / 128), 128, 0, k.stream>>>(d_grid, d_cs, d_sorted, d_src, (int)n, use_gicp_covariances ? 1 : 0,
+                                                                     reinterpret_cast<float*>(k.D + o_sc));
+  k_grid_build<<<1, kThreads, 0, k.stream>>>(d_dst, (int)m, grid_cell, d_cs, d_cf, d_sorted, d_grid);   // stays: the NN target
+  k_covariances<<<(unsigned)((m + 127) / 128), 128, 0, k.stream>>>(d_grid, d_cs, d_sorted, d_dst, (int)m, use_gicp_covariances ? 1 : 0,
+                                                                     reinterpret_cast<float*>(k.D + o_dc));
+  launches += 4;
+  for (int outer = 0; outer < max_outer; ++outer) {
+    // tmp = estimate * src; FindCorrespondences(dst_tree, tmp) (:149-150,160)
+    k_transform_points<<<(unsigned)((n + 255) / 256), 256, 0, k.stream>>>(d_src, (int)n, ds->pose_cm, reinterpret_cast<float*>(k.D + o_tmp));
+    k_nn_query<<<(unsigned)((n + 127) / 128), 128, 0, k.stream>>>(d_grid, d_cs, d_sorted, reinterpret_cast<const float*>(k.D + o_tmp), (int)n,
+                                                                    reinterpret_cast<int*>(k.D + o_idx), reinterpret_cast<float*>(k.D + o_d2));
+    launches += 2;
+    for (int it = 0; it < inner_iters; ++it) {
+      k_gicp_residuals<<<n_blocks, kGicpThreads, 0, k.stream>>>(d_src, d_dst, reinterpret_cast<const float*>(k.D + o_sc),
+                                                                reinterpret_cast<const float*>(k.D + o_dc), reinterpret_cast<const int*>(k.D + o_idx),
+                                                                (int)n, (int)m, ds->pose_cm, huber_delta, nullptr, reinterpret_cast<double*>(k.D + o_part));
+      k_gicp_finish<<<1, 32, 0, k.stream>>>(reinterpret_cast<const double*>(k.D + o_part), n_blocks, ds, it == 0 ? 2 : 1);
+      launches += 2;
+    }
+  }
+  // statistics of the final pose over the last correspondences
+  if (max_outer > 0) {
+    k_gicp_residuals<<<n_blocks, kGicpThreads, 0, k.stream>>>(d_src, d_dst, reinterpret_cast<const float*>(k.D + o_sc),
+                                                              reinterpret_cast<const float*>(k.D + o_dc), reinterpret_cast<const int*>(k.D + o_idx),
+                                                              (int)n, (int)m, ds->pose_cm, huber_delta, nullptr, reinterpret_cast<double*>(k.D + o_part));
+    k_gicp_finish<<<1, 32, 0, k.stream>>>(reinterpret_cast<const double*>(k.D + o_part), n_blocks, ds, 3);
+    launches += 2;
+  }
+  CLOUD_TRY(k.cuda(cudaGetLastError(), "launch"));
+  rst::ctx_count_launches(c, launches);
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.H + o_state, k.D + o_state, sizeof(GicpState), cudaMemcpyDeviceToHost, k.stream), "D2H"));
+  CLOUD_TRY(k.cuda(cudaStreamSynchronize(k.stream), "sync"));
+  std::memcpy(pose_inout, hs->pose_cm, 64);
+  if (stats_out) {
+    for (int i = 0; i < 21; ++i) stats_out->A[i] = hs->sums[i];
+    for (int i = 0; i < 6; ++i) stats_out->b[i] = hs->sums[21 + i];
+    stats_out->cost = hs->sums[27];
+    stats_out->count = (int32_t)hs->sums[28];
+  }
   return RST_OK;
 }

@@ -1,0 +1,111 @@
+// The reference's own call expressions, verbatim, against include/rs_tracker/align/align_rgbd.hpp. Test code: built
+// in the build container by `make -C oracle ref` (it includes the reference's own rs_tracker/common/types.hpp for
+// Cloud3f / KDTree3f, and the stand-in Eigen / ChoUtil / nanoflann headers of oracle/shim) into
+// oracle/_ref/literal_calls, and run on the GPU box by tests/test_cpp_api.py.
+//   rs_replay_app.cpp:245-251   DownsampleVoxel(cloud, 0.05f, &curr_cloud_down); AlignIcp3d(curr_cloud_down, prev_cloud_down, 128, &xfm)
+//   rs_align_app.cpp:295        SolveKabsch(src_cloud, dst_cloud, indices, weights, &xfm)
+//   rs_align_app.cpp:303        AlignIcp3d(src_cloud, dst_cloud, 128, &xfm)
+//   align_icp.cpp:165-166       AlignIcp3d(src, dst, dst_tree, max_iter, transform)
+//   point_cloud_utils.hpp:14    FindCorrespondences(tree, source, &indices, &squared_distances)
+#include <cmath>
+#include <cstdio>
+#include <random>
+
+#include "rs_tracker/common/types.hpp"       // the reference's own header: Cloud3f, KDTree3f
+#include "rs_tracker/align/align_rgbd.hpp"   // instead of rs_tracker/align/align_icp.hpp + common/point_cloud_utils.hpp
+
+static float translation_error(const Eigen::Isometry3f& x, const float* t) {
+  const float* m = x.matrix().data();   // column-major 4x4
+  const float dx = m[12] - t[0], dy = m[13] - t[1], dz = m[14] - t[2];
+  return std::sqrt(dx * dx + dy * dy + dz * dz);
+}
+
+int main() {
+  std::mt19937 rng(11);
+  std::uniform_real_distribution<float> U(-1.f, 1.f);
+  rs_tracker::Cloud3f src_cloud, dst_cloud;
+  const int n = 2000;
+  src_cloud.SetNumPoints(n);
+  dst_cloud.SetNumPoints(n);
+  // dst = R_x(0.02) R_y(-0.04) R_z(0.05) src + t   (the reference's disabled self-test, rs_align_app.cpp:257-263, scaled)
+  const float rx = 0.02f, ry = -0.04f, rz = 0.05f;
+  const float cxr = std::cos(rx), sxr = std::sin(rx), cyr = std::cos(ry), syr = std::sin(ry), czr = std::cos(rz), szr = std::sin(rz);
+  const float R[9] = {cyr * czr, -cyr * szr, syr,
+                      sxr * syr * czr + cxr * szr, -sxr * syr * szr + cxr * czr, -sxr * cyr,
+                      -cxr * syr * czr + sxr * szr, cxr * syr * szr + sxr * czr, cxr * cyr};
+  const float t[3] = {0.05f, -0.03f, 0.02f};
+  float* s = src_cloud.GetPtr();
+  float* d = dst_cloud.GetPtr();
+  for (int i = 0; i < n; ++i) {
+    const float p[3] = {U(rng), U(rng), U(rng)};
+    for (int a = 0; a < 3; ++a) {
+      s[3 * i + a] = p[a];
+      d[3 * i + a] = R[3 * a] * p[0] + R[3 * a + 1] * p[1] + R[3 * a + 2] * p[2] + t[a];
+    }
+  }
+  int failures = 0;
+
+  // rs_align_app.cpp:290-303
+  std::vector<std::pair<int, int>> indices;
+  std::vector<float> weights;
+  for (int i = 0; i < n; i += 3) indices.emplace_back(i, i);
+  Eigen::Isometry3f xfm = Eigen::Isometry3f::Identity();
+  {
+    const bool suc =
+        rs_tracker::SolveKabsch(src_cloud, dst_cloud, indices, weights, &xfm);
+    if (!suc) { std::printf("kabsch failed\n"); ++failures; }
+  }
+  const float ek = translation_error(xfm, t);
+  std::printf("kabsch translation error %.3e\n", ek);
+  if (!(ek < 1e-4f)) ++failures;
+  {
+    const bool suc = rs_tracker::AlignIcp3d(src_cloud, dst_cloud, 128, &xfm);
+    if (!suc) { std::printf("icp failed\n"); ++failures; }
+  }
+  const float ei = translation_error(xfm, t);
+  std::printf("icp translation error %.3e\n", ei);
+  if (!(ei < 1e-3f)) ++failures;
+
+  // rs_replay_app.cpp:245-251
+  {
+    const rs_tracker::Cloud3f& cloud = src_cloud;
+    const rs_tracker::Cloud3f& prev_cloud = dst_cloud;
+    Eigen::Isometry3f xfm = Eigen::Isometry3f::Identity();
+    cho::core::PointCloud<float, 3> curr_cloud_down, prev_cloud_down;
+    rs_tracker::DownsampleVoxel(cloud, 0.05f, &curr_cloud_down);
+    rs_tracker::DownsampleVoxel(prev_cloud, 0.05f, &prev_cloud_down);
+    bool suc{false};
+    suc =
+        rs_tracker::AlignIcp3d(curr_cloud_down, prev_cloud_down, 128, &xfm);
+    std::printf("replay-style: %d -> %d / %d points, suc %d\n", n, curr_cloud_down.GetNumPoints(), prev_cloud_down.GetNumPoints(), (int)suc);
+    if (!suc || curr_cloud_down.GetNumPoints() < 3 || curr_cloud_down.GetNumPoints() > n) ++failures;
+  }
+
+  // align_icp.cpp:163-167 (the 5-argument form) and point_cloud_utils.hpp:14
+  {
+    const rs_tracker::KDTree3f dst_tree{std::cref(dst_cloud), 16};
+    Eigen::Isometry3f x2 = Eigen::Isometry3f::Identity();
+    const bool suc = rs_tracker::AlignIcp3d(src_cloud, dst_cloud, dst_tree, 128, &x2);
+    if (!suc || translation_error(x2, t) > 1e-3f) { std::printf("5-argument form failed\n"); ++failures; }
+    std::vector<int> idx;
+    std::vector<float> d2;
+    rs_tracker::FindCorrespondences(dst_tree, src_cloud, &idx, &d2);
+    int cpu_idx[1];
+    float cpu_d2[1];
+    int bad = 0;
+    for (int i = 0; i < n; i += 97) {
+      dst_tree.query(s + 3 * i, 1, cpu_idx, cpu_d2);
+      if (cpu_idx[0] != idx[i] || cpu_d2[0] != d2[i]) ++bad;
+    }
+    std::printf("FindCorrespondences: %zu results, %d mismatches against the k-d tree\n", idx.size(), bad);
+    if ((int)idx.size() != n || bad) ++failures;
+    rs_tracker::Cloud3f with_nan, clean;
+    with_nan.SetNumPoints(n);
+    for (int i = 0; i < 3 * n; ++i) with_nan.GetPtr()[i] = s[i];
+    with_nan.GetPtr()[3 * 5 + 1] = std::nanf("");
+    rs_tracker::RemoveNans(with_nan, &clean);
+    if (clean.GetNumPoints() != n - 1) { std::printf("RemoveNans kept %d\n", clean.GetNumPoints()); ++failures; }
+  }
+  std::printf("failures %d\n", failures);
+  return failures;
+}

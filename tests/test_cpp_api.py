@@ -42,3 +42,26 @@ def test_eigen_overload_compiles_against_the_stand_in_eigen(tmp_path):
     res = subprocess.run(["/usr/bin/g++", "-std=c++17", "-fsyntax-only", "-I", str(ROOT / "include"), "-I", str(ROOT / "oracle" / "shim"), str(src)],
                          capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
+
+
+LITERAL = ROOT / "oracle" / "_ref" / "literal_calls"
+
+
+def test_reference_call_sites_compile_verbatim():
+    """rs_replay_app.cpp:246-251, rs_align_app.cpp:295,303, align_icp.cpp:165 and point_cloud_utils.hpp:14 as written
+    there (tests/cpp/literal_calls.cpp) compile against align_rgbd.hpp with the reference's own types.hpp supplying
+    Cloud3f / KDTree3f. Needs /root/reference (build container only); the binary travels in oracle/_ref."""
+    from pathlib import Path
+    if not Path("/root/reference/rs_tracker/common/include/rs_tracker/common/types.hpp").exists():
+        pytest.skip("the reference tree is not mounted here")
+    res = subprocess.run(["make", "-C", str(ROOT / "oracle"), "_ref/literal_calls"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert LITERAL.exists()
+
+
+@pytest.mark.gpu
+def test_reference_call_sites_run_on_the_gpu():
+    if not LITERAL.exists():
+        pytest.skip("oracle/_ref/literal_calls was not built (needs the reference tree at build time)")
+    res = subprocess.run([str(LITERAL)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "failures 0" in res.stdout, res.stdout + res.stderr

@@ -95,3 +95,77 @@ def test_stress_invalid_depth_large_motion_huber():
         assert dt < 1e-4 and dr < 1e-4, (dt, dr)
     finally:
         al.close()
+
+
+def test_config4_848x480_rgbd_frame_to_keyframe_photometric_parity():
+    """BASELINE config 4 at its own size: 848x480 RGB-D, frames 1..3 against keyframe 0, geometric + photometric
+    residual (lambda = 0.5). Intensity pyramid and association bit-exact, normal equations 1e-4 at the finest level,
+    final poses within 1e-4 m / 1e-4 rad of the CPU specification, known motion recovered."""
+    w, h = 848, 480
+    intr = synth.intrinsics_for(w, h)
+    sc = synth.Scene(4)
+    Twc = synth.trajectory(4, seed=4)
+    fr = [sc.render(Twc[k], w, h, intr=intr, rgb=True) for k in range(4)]
+    depth = np.stack([f[0] for f in fr]); rgb = np.stack([f[1] for f in fr])
+    kw = dict(photo_weight=0.5)
+    P, Po = default_params(**kw), O.default_params(**kw)
+    al = Aligner(w, h, 6, 3)
+    try:
+        al.begin(w, h, intr, P)
+        al.upload(depth, rgb=rgb)
+        al.preprocess(0, 4)
+        I = O.intensity(rgb[2])
+        for l in range(3):
+            assert np.array_equal(al.read_intensity(2, l).view(np.uint32), I.view(np.uint32)), f"intensity level {l}"
+            I = O.intensity_down(I)
+        L0 = O.level_info(intr, w, h, 0)
+        T = np.eye(4)
+        idx_o, st_o = O.evaluate_photo(depth[2], None, O.geometry(depth[0], L0, Po), O.intensity(rgb[2]), O.intensity(rgb[0]), L0, Po, T)
+        idx_g, st_g = al.evaluate(2, 0, 0, T)
+        assert np.array_equal(idx_g, idx_o)
+        Ao, Ag = np.array(st_o.A[:]), np.array(st_g.A[:])
+        assert np.max(np.abs(Ag - Ao)) <= 1e-4 * np.max(np.abs(Ao))
+        assert abs(st_g.sum_wr2 - st_o.sum_wr2) <= 1e-4 * st_o.sum_wr2
+        Tg, st = al.align_pairs(depth[[1, 2, 3]], depth[[0, 0, 0]], intr, P, src_rgb=rgb[[1, 2, 3]], dst_rgb=rgb[[0, 0, 0]])
+        for i, k in enumerate((1, 2, 3)):
+            gt = synth.relative_pose(Twc[0], Twc[k])
+            et, er = synth.pose_error(Tg[i], gt)
+            assert st[i].status == 0 and et < 2e-3 and er < 2e-3, (k, et, er)
+        To, so = O.align_pair_rgbd(depth[3], depth[0], rgb[3], rgb[0], intr, Po)
+        dt, dr = synth.pose_error(Tg[2], To)
+        assert dt < 1e-4 and dr < 1e-4, (dt, dr)
+    finally:
+        al.close()
+
+
+def test_config5_1280x720_huber_normal_gate_invalid_depth_parity():
+    """BASELINE config 5 ingredients at 1280x720: 30 % invalid depth, Huber weights and the source/target normal
+    gate. Association bit-exact and normal equations 1e-4 on all three levels, final pose 1e-4 vs the specification."""
+    w, h = 1280, 720
+    intr = synth.intrinsics_for(w, h)
+    noise = synth.Noise(p_invalid_pixel=0.21, p_invalid_block=0.12)
+    src, dst, gt = synth.render_pairs(2, w, h, seed=13, max_t=0.06, max_r=np.deg2rad(4.0), noise=noise)
+    kw = dict(robust_kind=N.RST_ROBUST_HUBER, robust_scale=0.01, normal_cos_min=0.8, dist_max=0.4, iters=[10, 8, 8, 0], num_levels=3)
+    P, Po = default_params(**kw), O.default_params(**kw)
+    al = Aligner(w, h, 4, 2)
+    try:
+        T, st = al.align_pairs(src, dst, intr, P)          # slots: dst 0..1, src 2..3
+        ds, dd = src[0], dst[0]
+        T0 = np.eye(4)
+        for l in range(3):
+            L = O.level_info(intr, w, h, l)
+            if l > 0:
+                ds, dd = O.pyr_down(ds, Po.pyr_depth_tol), O.pyr_down(dd, Po.pyr_depth_tol)
+            idx_o, st_o = O.evaluate(ds, O.geometry(ds, L, Po), O.geometry(dd, L, Po), L, Po, T0)
+            idx_g, st_g = al.evaluate(2, 0, l, T0)
+            assert np.array_equal(idx_g, idx_o), (l, int((idx_g != idx_o).sum()))
+            Ao, Ag = np.array(st_o.A[:]), np.array(st_g.A[:])
+            assert np.max(np.abs(Ag - Ao)) <= 1e-4 * np.max(np.abs(Ao)), l
+        for i in range(2):
+            et, er = synth.pose_error(T[i], gt[i])
+            assert st[i].status == 0 and et < 5e-3 and er < 5e-3, (i, et, er)
+        To, so = O.align_pair(src[0], dst[0], intr, Po)
+        dt, dr = synth.pose_error(T[0], To)
+        assert dt < 1e-4 and dr < 1e-4, (dt, dr)
+    finally:
+        al.close()

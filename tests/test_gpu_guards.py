@@ -1,0 +1,110 @@
+"""GPU: robustness of the entry points (round-1 advisor findings): non-finite cloud inputs, slot ranges of
+device-bound frames, one outstanding asynchronous call per context, and the success criterion of a pair whose
+coarse level failed."""
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import oracle as O
+from realsensetracker_b200 import Aligner, default_params, synth
+from realsensetracker_b200 import _native as N
+from realsensetracker_b200.align import RstError
+
+pytestmark = pytest.mark.gpu
+GOLD = np.load(ROOT / "tests" / "golden" / "oracle_r.npz")
+
+
+def test_cloud_icp_survives_non_finite_points_and_poses():
+    """A NaN/Inf source point or initial pose has no nearest neighbour: the call must report failure (ok = 0), never
+    read out of bounds, and leave the context usable (the reference's callers run RemoveNans first,
+    rs_replay_app.cpp:246)."""
+    src, dst = GOLD["src"].copy(), GOLD["dst"]
+    al = Aligner(16, 16, 2, 1)
+    try:
+        bad = src.copy(); bad[5] = np.nan; bad[17, 1] = np.inf
+        ok, T = al.icp3d_pairs([bad], [dst], 8)
+        assert not ok[0]
+        T0 = np.eye(4); T0[0, 3] = np.nan
+        ok, T = al.icp3d_pairs([src], [dst], 8, T0=T0)
+        # iteration 0 finds no neighbour for any point (all weights 0 -> zero covariance -> R = I, t = centroid
+        # difference), after which the iterations proceed from a finite pose: either outcome is fine, a fault is not
+        assert (not ok[0]) or np.isfinite(T[0]).all()
+        bad_dst = dst.copy(); bad_dst[3] = np.nan
+        ok, T = al.icp3d_pairs([src], [bad_dst], 8)          # a NaN target point is never anybody's neighbour
+        assert np.isfinite(T[0]).all()
+        ok, T = al.icp3d_pairs([src], [dst], 128)            # the context still works, and still gets the right answer
+        ok_o, T_o = O.align_icp3d(src, dst, 128)
+        assert ok[0] and ok_o
+        dt, dr = synth.pose_error(T[0], T_o)
+        assert dt < 1e-4 and dr < 1e-4
+    finally:
+        al.close()
+
+
+def test_device_bound_frames_reject_slots_outside_the_bound_range(seq_small):
+    import torch
+    frames, gt, intr = seq_small
+    n, h, w = frames.shape
+    pitch = (w + 7) // 8 * 8
+    buf = torch.zeros((2, h, pitch), dtype=torch.int16, device="cuda")
+    buf[:, :, :w] = torch.from_numpy(frames[:2].view(np.int16)).cuda()
+    al = Aligner(w, h, 8, 4)
+    try:
+        P = default_params()
+        al.begin(w, h, intr, P)
+        al.set_frames_device(buf.data_ptr(), 2, pitch, pitch * h, first_slot=2)      # slots 2 and 3 only
+        al.preprocess(2, 2)
+        T, st = al.align_slots([3], [2])
+        assert st[0].status == 0
+        with pytest.raises(RstError):
+            al.preprocess(0, 2)                                                      # slots 0, 1 are not backed by anything
+        with pytest.raises(RstError):
+            al.align_slots([3], [1])
+        with pytest.raises(RstError):
+            al.evaluate(4, 2, 0, np.eye(4))
+    finally:
+        al.close()
+
+
+def test_one_outstanding_async_call_per_context(seq_small):
+    frames, gt, intr = seq_small
+    n, h, w = frames.shape
+    al = Aligner(w, h, n, n - 1)
+    try:
+        P = default_params()
+        al.submit_sequence(frames, intr, P)
+        with pytest.raises(RstError):
+            al.submit_sequence(frames, intr, P)          # would overwrite staging an enqueued copy still uses
+        with pytest.raises(RstError):
+            al.align_sequence(frames, intr, P)
+        T, st = al.wait()
+        T2, _ = al.align_sequence(frames, intr, P)       # after rst_wait the context is free again
+        assert np.array_equal(T, T2)
+    finally:
+        al.close()
+
+
+def test_failed_coarse_level_does_not_fail_a_pair_that_converged():
+    """Sparse depth: the coarsest level has fewer associations than min_count (TOO_FEW), the finer levels converge.
+    status (the success criterion) is the LAST evaluated iteration; the failure stays visible in any_status /
+    failed_iterations. Same semantics as the CPU specification."""
+    w, h = 160, 120
+    intr = (96.0, 96.0, 80.0, 60.0)
+    sc = synth.Scene(7)
+    Twc = synth.trajectory(2, seed=7, step_t=0.01, step_r=0.008)
+    frames = np.stack([sc.render(Twc[k], w, h, intr=intr) for k in range(2)])
+    gt = synth.relative_pose(Twc[0], Twc[1])
+    kw = dict(min_count=900)                                      # level 2 is 40x30 = 1200 px: fewer than 900 carry a normal
+    P, Po = default_params(**kw), O.default_params(**kw)
+    To, so = O.align_pair(frames[1], frames[0], intr, Po)
+    assert so.status == 0 and so.any_status == N.RST_STATUS_TOO_FEW and so.failed_iterations == Po.iters[2]
+    al = Aligner(w, h, 2, 1)
+    try:
+        T, st = al.align_sequence(frames, intr, P)
+        assert st[0].status == 0 and st[0].any_status == N.RST_STATUS_TOO_FEW
+        assert st[0].failed_iterations == so.failed_iterations and st[0].iterations == so.iterations
+        dt, dr = synth.pose_error(T[0], To)
+        assert dt < 1e-4 and dr < 1e-4
+        assert synth.pose_error(T[0], gt)[0] < 3e-3
+    finally:
+        al.close()

@@ -64,6 +64,10 @@ def test_random_inputs_stay_bit_exact(seed):
             if st_o.count > 50:
                 Ao, Ag = np.array(st_o.A[:]), np.array(st_g.A[:])
                 assert np.max(np.abs(Ag - Ao)) <= 1e-4 * np.max(np.abs(Ao)), (seed, l)
+                # J^T r against the size of its summands, sqrt(A_kk * sum w r^2) (see test_gpu_parity.jtr_error)
+                bo, bg = np.array(st_o.b[:]), np.array(st_g.b[:])
+                scale = np.sqrt(np.maximum(Ao[[0, 6, 11, 15, 18, 20]] * st_o.sum_wr2, 1e-300))
+                assert np.max(np.abs(bg - bo) / scale) <= 1e-4, (seed, l, "J^T r")
                 assert abs(st_g.sum_wr2 - st_o.sum_wr2) <= 1e-4 * st_o.sum_wr2 + 1e-12
         # the full loop never crashes and reports a status consistent with the oracle's
         Tg, st = al.align_pairs(frames[1:2], frames[0:1], intr, P, T0=T)
