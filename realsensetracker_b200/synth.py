@@ -127,13 +127,15 @@ def render_sequence(n_frames: int, w: int, h: int, seed: int = 0, noise: Noise |
 
 
 def render_pairs(n_pairs: int, w: int, h: int, seed: int = 0, max_t: float = 0.03, max_r: float = np.deg2rad(2.0),
-                 noise: Noise | None = None):
+                 noise: Noise | None = None, first: int = 0, out=None):
     """Independent pairs with per-pair random motion: returns
-    src [n,h,w], dst [n,h,w], gt [n,4,4] with p_dst = gt p_src."""
-    src = np.empty((n_pairs, h, w), dtype=np.uint16)
-    dst = np.empty((n_pairs, h, w), dtype=np.uint16)
+    src [n,h,w], dst [n,h,w], gt [n,4,4] with p_dst = gt p_src. Pair k of the call is pair `first + k` of the
+    seed's global list (a rank renders exactly its block of a sharded batch); `out` = (src, dst) buffers to fill."""
+    src = out[0] if out is not None else np.empty((n_pairs, h, w), dtype=np.uint16)
+    dst = out[1] if out is not None else np.empty((n_pairs, h, w), dtype=np.uint16)
     gt = np.empty((n_pairs, 4, 4))
-    for i in range(n_pairs):
+    for k in range(n_pairs):
+        i = first + k
         rng = np.random.default_rng(seed * 7919 + i)
         scene = Scene(seed * 7919 + i + 1)
         base = make_pose(rotvec_to_R(rng.normal(size=3) * 0.05), rng.uniform(-0.3, 0.3, size=3))
@@ -141,7 +143,7 @@ def render_pairs(n_pairs: int, w: int, h: int, seed: int = 0, max_t: float = 0.0
         a = rng.normal(size=3); a *= rng.uniform(0.3, 1.0) * max_r / np.linalg.norm(a)
         T_dst = base
         T_src = base @ make_pose(rotvec_to_R(a), d)
-        scene.render(T_dst, w, h, noise=noise, frame_seed=2 * i, out=dst[i])
-        scene.render(T_src, w, h, noise=noise, frame_seed=2 * i + 1, out=src[i])
-        gt[i] = relative_pose(T_dst, T_src)
+        scene.render(T_dst, w, h, noise=noise, frame_seed=2 * i, out=dst[k])
+        scene.render(T_src, w, h, noise=noise, frame_seed=2 * i + 1, out=src[k])
+        gt[k] = relative_pose(T_dst, T_src)
     return src, dst, gt
