@@ -697,7 +697,8 @@ def run_extra_configs(args, rank, world, local_rank, dev, stream, peak):
         with torch.cuda.stream(stream):
             al.copy_results_device(None, d_stats.data_ptr())
         torch.cuda.synchronize()
-        C.memmove(C.addressof(st), d_stats.cpu().numpy().ctypes.data, n * C.sizeof(N.Stats))
+        h_stats_raw = d_stats.cpu().numpy()      # keep the host array alive across the memmove
+        C.memmove(C.addressof(st), h_stats_raw.ctypes.data, n * C.sizeof(N.Stats))
         count = float(np.mean([s.count for s in st])) if n else 0.0
         failed = sum(1 for s in st if s.status != 0)
         t_l0 = prof.ms_icp[0] * 1e-3 / max(prof.launches_icp[0], 1)
