@@ -74,7 +74,7 @@ enum {
  * tilings differ from each other in the last bits (different fp32 partial-sum extents). */
 enum {
   RST_TILING_THROUGHPUT = 0,  /* up to 8192 pixels per block: fewest partials, best for batches   */
-  RST_TILING_LATENCY = 1      /* 512 pixels per block: a single pair spreads over all 148 SMs      */
+  RST_TILING_LATENCY = 1      /* about 148 blocks per pair and level: a single pair fills the GPU in one wave */
 };
 
 /* ---- launch schedule of the iteration loop (rst_set_schedule) ---- */
@@ -217,6 +217,11 @@ int32_t rst_set_pipeline_chunk(rst_ctx* ctx, int32_t frames_per_chunk);
  * levels of the other. min_pairs <= 0 disables the split (single stream; used when timing one kernel in
  * isolation). Never changes results. */
 int32_t rst_set_stream_split(rst_ctx* ctx, int32_t min_pairs);
+
+/* Blocking host-frame calls (rst_align_pairs / rst_align_sequence) with at most `max_pairs` pairs (default 8) run
+ * their kernels as ONE replayed CUDA graph (captured per frame size / parameter set / pair count): the single-pair
+ * latency path. 0 disables it. Never changes results. */
+int32_t rst_set_graph_max_pairs(rst_ctx* ctx, int32_t max_pairs);
 
 /* Selects how the iteration loop is launched (RST_SCHEDULE_*). Poses agree between the two schedules to fp32
  * round-off of the partial-sum extents; each schedule is bit-reproducible. */

@@ -332,6 +332,10 @@ class Aligner:
     def set_stream_split(self, min_pairs: int):
         self._check(self._lib.rst_set_stream_split(self._ctx, min_pairs))
 
+    def set_graph_max_pairs(self, max_pairs: int):
+        """Blocking host-frame calls with at most this many pairs replay a CUDA graph (default 8; 0 = never)."""
+        self._check(self._lib.rst_set_graph_max_pairs(self._ctx, max_pairs))
+
     def set_schedule(self, schedule: int):
         """0 = fused (one cluster per pair, all iterations in one launch; default), 1 = one launch per iteration."""
         self._check(self._lib.rst_set_schedule(self._ctx, schedule))

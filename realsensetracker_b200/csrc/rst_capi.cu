@@ -84,6 +84,18 @@ struct rst_ctx {
   int pipeline_chunk = 0;               // frames (pairs) per upload/compute chunk of the host entry points
   void* ext = nullptr;                  // state of the cloud-based engine (rst_icp3d.cu), created on first use
   void (*ext_free)(void*) = nullptr;
+  // CUDA graphs of the kernel part of small blocking calls (the latency path): a replay costs one enqueue instead
+  // of ~27 and removes the launch gaps between the 23 dependent kernels of a pair
+  struct GraphKey {
+    int32_t mode, w, h, n_frames, n_pairs, schedule;   // mode 0: sequence, 1: pairs
+    rst_intrinsics K;
+    rst_params P;
+  };
+  struct CachedGraph { GraphKey key; cudaGraphExec_t exec; int launches; uint64_t stamp; };
+  std::vector<CachedGraph> graphs;
+  int pdl_max_pairs = 8;                // batches up to this size chain their iteration launches with programmatic dependent launch
+  int graph_max_pairs = 8;              // blocking calls with at most this many pairs replay a graph (0 = never)
+  uint64_t graph_clock = 0;
   int n_pairs_last = 0;
   int fetch_pending = 0;                // pairs whose results sit in the pinned staging of an *_async call
   int64_t launches = 0;
@@ -188,6 +200,7 @@ void rst_ctx_destroy(rst_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
   if (c->ext && c->ext_free) c->ext_free(c->ext);
   for (int l = 0; l < RST_MAX_LEVELS; ++l) { cudaFree(c->d_depth[l]); cudaFree(c->d_geom[l]); }
   cudaFree(c->d_pairs); cudaFree(c->d_poses_in); cudaFree(c->d_master); cudaFree(c->d_pose_f32);
@@ -281,6 +294,7 @@ int32_t rst_ctx_create(int32_t device, int32_t max_w, int32_t max_h, int32_t max
     const int v = std::atoi(e);
     if (v >= 1 && v <= 16) c->cluster_size[0] = c->cluster_size[1] = v;
   }
+  if (const char* e = std::getenv("RST_PDL_MAX_PAIRS")) c->pdl_max_pairs = std::atoi(e);
   if (const char* e = std::getenv("RST_SCHEDULE")) {
     const int v = std::atoi(e);
     if (v >= RST_SCHEDULE_AUTO && v <= RST_SCHEDULE_HYBRID) c->schedule = v;
@@ -323,7 +337,13 @@ int32_t rst_begin(rst_ctx* c, int32_t width, int32_t height, const rst_intrinsic
       // pixels per block ~ level size / 8, a power-of-two number of groups, at most kMaxGroups
       const int group_px = kChunksPerBlock * kChunkPx;
       int g = 1;
-      while (P.tiling != RST_TILING_LATENCY && g * 2 <= kMaxGroups && (int64_t)g * 2 * group_px * 8 <= (int64_t)c->n_chunks[l] * kChunkPx) g *= 2;
+      if (P.tiling != RST_TILING_LATENCY) {
+        while (g * 2 <= kMaxGroups && (int64_t)g * 2 * group_px * 8 <= (int64_t)c->n_chunks[l] * kChunkPx) g *= 2;
+      } else {
+        // latency tiling: the smallest blocks that still give one pair about one block per SM (148): a single pair
+        // fills the GPU in one wave and the last block sums ~150 partials instead of 600
+        while (g * 2 <= kMaxGroups && (int64_t)g * 2 * group_px * 148 <= (int64_t)c->n_chunks[l] * kChunkPx) g *= 2;
+      }
       c->groups[l] = g;
     }
     const int cpb = kChunksPerBlock * c->groups[l];
@@ -548,9 +568,20 @@ static int32_t link_streams(rst_ctx* c, cudaStream_t from, cudaStream_t to) {  /
   return RST_OK;
 }
 
-/* stage 1 of an alignment: pair table + initial poses -> device, state reset */
+/* device half of stage 1: the staged pair table + initial poses -> device, state reset */
+static int32_t pairs_begin_enqueue(rst_ctx* c, int32_t n_pairs) {
+  RST_CUDA(c, cudaMemcpyAsync(c->d_pairs, c->h_pairs, sizeof(int2) * n_pairs, cudaMemcpyHostToDevice, c->stream));
+  RST_CUDA(c, cudaMemcpyAsync(c->d_poses_in, c->h_poses, sizeof(float) * 16 * n_pairs, cudaMemcpyHostToDevice, c->stream));
+  InitArgs ia{c->d_poses_in, c->d_master, c->d_pose_f32, c->d_poses_cm, c->d_stats, c->d_tickets, n_pairs};
+  RST_CUDA(c, launch_init_pairs(ia, c->stream));
+  c->launches += 1;
+  return RST_OK;
+}
+
+/* stage 1 of an alignment: pair table + initial poses into the pinned staging (and, unless the caller replays a
+ * graph that contains it, on to the device) */
 static int32_t pairs_begin(rst_ctx* c, const int32_t* src_slots, const int32_t* dst_slots, int32_t n_pairs,
-                           const float* poses_in) {
+                           const float* poses_in, bool enqueue = true) {
   if (check_idle(c) != RST_OK) return RST_ERR_INVALID_ARG;   // the pinned staging below still belongs to that call
   for (int i = 0; i < n_pairs; ++i) {
     if (!slot_bound(c, src_slots[i]) || !slot_bound(c, dst_slots[i]))
@@ -563,13 +594,8 @@ static int32_t pairs_begin(rst_ctx* c, const int32_t* src_slots, const int32_t* 
     for (int i = 0; i < n_pairs; ++i)
       for (int k = 0; k < 16; ++k) c->h_poses[16 * i + k] = (k % 5 == 0) ? 1.f : 0.f;
   }
-  RST_CUDA(c, cudaMemcpyAsync(c->d_pairs, c->h_pairs, sizeof(int2) * n_pairs, cudaMemcpyHostToDevice, c->stream));
-  RST_CUDA(c, cudaMemcpyAsync(c->d_poses_in, c->h_poses, sizeof(float) * 16 * n_pairs, cudaMemcpyHostToDevice, c->stream));
-  InitArgs ia{c->d_poses_in, c->d_master, c->d_pose_f32, c->d_poses_cm, c->d_stats, c->d_tickets, n_pairs};
-  RST_CUDA(c, launch_init_pairs(ia, c->stream));
-  c->launches += 1;
   c->n_pairs_last = n_pairs;
-  return RST_OK;
+  return enqueue ? pairs_begin_enqueue(c, n_pairs) : RST_OK;
 }
 
 /* stage 2, fused schedule: ONE launch runs every iteration of every level for pairs [first, first + n);
@@ -634,6 +660,10 @@ static int32_t pairs_iterate(rst_ctx* c, int first, int n) {
     if (a.done) RST_CUDA(c, cudaMemsetAsync(c->d_done + first, 0, (size_t)n, c->stream));  // every level starts active
     const int ph = prof_begin(c, 1, l);
     int nl = 0;
+    // small batches (the latency path): consecutive iteration launches overlap head and tail (programmatic dependent
+    // launch); large batches keep plain stream order — there the early blocks of the next launch would only take
+    // SM slots from the running one
+    a.pdl = (c->pdl_max_pairs > 0 && n <= c->pdl_max_pairs && !c->profiling) ? 1 : 0;
     for (int it = 0; it < c->P.iters[l]; ++it) {
       for (int off = 0; off < n; off += 65535) {
         a.pair_offset = first + off;
@@ -692,6 +722,77 @@ static int32_t pairs_fetch(rst_ctx* c, int32_t n_pairs, float* poses_out, rst_st
   int32_t rc = fetch_enqueue(c, n_pairs);
   if (rc != RST_OK) return rc;
   return fetch_finish(c, poses_out, stats_out);
+}
+
+/* The kernel part of a small blocking host-frame call as one CUDA graph: pair table / pose upload, state reset, the
+ * pre-processing launches, every iteration launch and the result copies into the pinned staging. Captured the first
+ * time a (mode, size, parameters, pair count) combination is seen, replayed afterwards; the frame upload stays outside
+ * (its source is caller memory). `pre` ranges: frames [0, n_frames) with geometry; for mode 1 the source frames
+ * [n_pairs, 2 n_pairs) get geometry only with the normal gate. Returns RST_OK with *ran = false when graphs do not
+ * apply (the caller then enqueues directly). */
+static int32_t run_graphed(rst_ctx* c, int mode, int n_frames, int n_pairs, bool* ran) {
+  *ran = false;
+  if (c->graph_max_pairs <= 0 || n_pairs > c->graph_max_pairs || c->profiling || c->ext0) return RST_OK;
+  rst_ctx::GraphKey key;
+  std::memset(&key, 0, sizeof(key));
+  key.mode = mode; key.w = c->w; key.h = c->h; key.n_frames = n_frames; key.n_pairs = n_pairs; key.schedule = c->schedule;
+  key.K = c->K; key.P = c->P;
+  rst_ctx::CachedGraph* hit = nullptr;
+  for (auto& g : c->graphs)
+    if (std::memcmp(&g.key, &key, sizeof(key)) == 0) { hit = &g; break; }
+  if (!hit) {
+    const int64_t launches0 = c->launches;
+    if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return RST_OK; }
+    int32_t rc = pairs_begin_enqueue(c, n_pairs);
+    const bool ngate = c->P.normal_cos_min > -1.0f;
+    if (rc == RST_OK) {
+      if (mode == 0) rc = preprocess_impl(c, 0, n_frames, true);
+      else {
+        rc = preprocess_impl(c, 0, n_pairs, true);
+        if (rc == RST_OK) rc = preprocess_impl(c, n_pairs, n_pairs, ngate);
+      }
+    }
+    if (rc == RST_OK) rc = pairs_iterate_split(c, n_pairs);
+    if (rc == RST_OK) {
+      // result copies (fetch_enqueue without the pending flag: set by the caller after the launch)
+      if (cudaMemcpyAsync(c->h_poses, c->d_poses_cm, sizeof(float) * 16 * n_pairs, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+          cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(rst_stats) * n_pairs, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+        rc = RST_ERR_CUDA;
+    }
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e_end = cudaStreamEndCapture(c->stream, &graph);
+    const int launches = (int)(c->launches - launches0);
+    c->launches = launches0;
+    if (rc != RST_OK || e_end != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return RST_OK;   // not captured: the direct path reports any real error
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t e_inst = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e_inst != cudaSuccess) { cudaGetLastError(); return RST_OK; }
+    if (c->graphs.size() >= 8) {   // drop the least recently used
+      size_t lru = 0;
+      for (size_t i = 1; i < c->graphs.size(); ++i) if (c->graphs[i].stamp < c->graphs[lru].stamp) lru = i;
+      cudaGraphExecDestroy(c->graphs[lru].exec);
+      c->graphs.erase(c->graphs.begin() + lru);
+    }
+    c->graphs.push_back({key, exec, launches, 0});
+    hit = &c->graphs.back();
+  }
+  hit->stamp = ++c->graph_clock;
+  RST_CUDA(c, cudaGraphLaunch(hit->exec, c->stream));
+  c->launches += hit->launches;
+  c->fetch_pending = n_pairs;
+  *ran = true;
+  return RST_OK;
+}
+
+int32_t rst_set_graph_max_pairs(rst_ctx* c, int32_t max_pairs) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  c->graph_max_pairs = max_pairs > 0 ? max_pairs : 0;
+  return RST_OK;
 }
 
 int32_t rst_align_slots(rst_ctx* c, const int32_t* src_slots, const int32_t* dst_slots, int32_t n_pairs,
@@ -823,10 +924,24 @@ static int32_t align_pairs_impl(rst_ctx* c, const rst_frame* src, const rst_fram
   // dst frames in slots [0, n), src frames in [n, 2n)
   std::vector<int32_t> s(n_pairs), d(n_pairs);
   for (int i = 0; i < n_pairs; ++i) { d[i] = i; s[i] = n_pairs + i; }
-  if ((rc = pairs_begin(c, s.data(), d.data(), n_pairs, poses_inout)) != RST_OK) return rc;
-  const bool ngate = c->P.normal_cos_min > -1.0f;
   const int chunk = c->pipeline_chunk > 0 && c->pipeline_chunk < n_pairs ? c->pipeline_chunk : n_pairs;
   const bool piped = chunk < n_pairs;
+  const bool try_graph = !piped && n_pairs <= c->graph_max_pairs && !c->profiling;
+  if ((rc = pairs_begin(c, s.data(), d.data(), n_pairs, poses_inout, !try_graph)) != RST_OK) return rc;
+  if (try_graph) {
+    if ((rc = rst_upload_frames(c, dst, n_pairs, 0)) != RST_OK) return rc;
+    if ((rc = rst_upload_frames(c, src, n_pairs, n_pairs)) != RST_OK) return rc;
+    bool ran = false;
+    if ((rc = run_graphed(c, 1, 2 * n_pairs, n_pairs, &ran)) != RST_OK) return rc;
+    if (ran) return wait ? fetch_finish(c, poses_inout, stats_out) : RST_OK;
+    if ((rc = pairs_begin_enqueue(c, n_pairs)) != RST_OK) return rc;   // graphs unavailable: the direct path, frames already uploaded
+    if ((rc = preprocess_impl(c, 0, n_pairs, true)) != RST_OK) return rc;
+    if ((rc = preprocess_impl(c, n_pairs, n_pairs, c->P.normal_cos_min > -1.0f)) != RST_OK) return rc;
+    if ((rc = pairs_iterate_split(c, n_pairs)) != RST_OK) return rc;
+    if (!wait) return fetch_enqueue(c, n_pairs);
+    return pairs_fetch(c, n_pairs, poses_inout, stats_out);
+  }
+  const bool ngate = c->P.normal_cos_min > -1.0f;
   cudaStream_t main_s = c->stream;
   if (piped) {
     if ((rc = link_streams(c, main_s, c->copy_stream)) != RST_OK) return rc;
@@ -877,9 +992,21 @@ static int32_t align_sequence_impl(rst_ctx* c, const rst_frame* frames, int32_t 
   const int n_pairs = n_frames - 1;
   std::vector<int32_t> s(n_pairs), d(n_pairs);
   for (int i = 0; i < n_pairs; ++i) { s[i] = i + 1; d[i] = i; }  // AlignIcp3d(curr, prev): rs_replay_app.cpp:251
-  if ((rc = pairs_begin(c, s.data(), d.data(), n_pairs, poses_inout)) != RST_OK) return rc;
   const int chunk = c->pipeline_chunk > 0 && c->pipeline_chunk < n_frames ? c->pipeline_chunk : n_frames;
   const bool piped = chunk < n_frames;
+  const bool try_graph = !piped && n_pairs <= c->graph_max_pairs && !c->profiling;
+  if ((rc = pairs_begin(c, s.data(), d.data(), n_pairs, poses_inout, !try_graph)) != RST_OK) return rc;
+  if (try_graph) {
+    if ((rc = rst_upload_frames(c, frames, n_frames, 0)) != RST_OK) return rc;
+    bool ran = false;
+    if ((rc = run_graphed(c, 0, n_frames, n_pairs, &ran)) != RST_OK) return rc;
+    if (ran) return wait ? fetch_finish(c, poses_inout, stats_out) : RST_OK;
+    if ((rc = pairs_begin_enqueue(c, n_pairs)) != RST_OK) return rc;   // graphs unavailable: the direct path, frames already uploaded
+    if ((rc = preprocess_impl(c, 0, n_frames, true)) != RST_OK) return rc;
+    if ((rc = pairs_iterate_split(c, n_pairs)) != RST_OK) return rc;
+    if (!wait) return fetch_enqueue(c, n_pairs);
+    return pairs_fetch(c, n_pairs, poses_inout, stats_out);
+  }
   cudaStream_t main_s = c->stream;
   if (piped) {
     if ((rc = link_streams(c, main_s, c->copy_stream)) != RST_OK) return rc;

@@ -475,7 +475,7 @@ k_icp_iter(const __grid_constant__ IcpArgs a) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pair = a.pair_offset + blockIdx.y;
-  if (EARLY) {  // convergence test on: this pair may have left the level already (block-uniform)
+  if (EARLY && !a.pdl) {  // convergence test on: this pair may have left the level already (block-uniform)
     if (a.done[pair]) return;
   }
   const int2 slots = a.pairs[pair];
@@ -495,7 +495,11 @@ k_icp_iter(const __grid_constant__ IcpArgs a) {
   pipe.P.depth_scale = a.depth_scale; pipe.P.dmax2 = a.dmax2; pipe.P.ncos_min = a.ncos_min;
   pipe.P.robust_scale = a.robust_scale; pipe.P.sqrt_lambda = a.sqrt_lambda; pipe.P.d_lo = a.d_lo; pipe.P.d_span = a.d_span;
   pipe.idx_out = WRITE_IDX ? a.idx_out + (int64_t)blockIdx.y * W * H : nullptr;
-  pipe.set_pose(a.pose_f32 + 12 * pair);
+  // Programmatic dependent launch (small batches, the latency path): the next iteration's launch may start while this
+  // one is still in its reduction / solve tail, and runs its pose-independent head (parameter setup, depth staging)
+  // under it; everything the previous launch writes (pose, done flag, tickets) is read after griddepcontrol.wait.
+  if (a.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (!a.pdl) pipe.set_pose(a.pose_f32 + 12 * pair);
   pipe.acc.clear();
   {  // first chunk of this warp in group 0; later chunks/groups are reached by adding strides
     const int c = blockIdx.x * a.groups * kChunksPerBlock + warp * kChunksPerWarp;
@@ -504,6 +508,13 @@ k_icp_iter(const __grid_constant__ IcpArgs a) {
   }
   stage_depth(s_d, Ds, a.lv.depth_pitch, W, H, a.chunks_per_row, a.cpr_magic, blockIdx.x * a.groups * kChunksPerBlock,
               a.groups * kChunksPerBlock, tid);
+  if (a.pdl) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (EARLY) {
+      if (a.done[pair]) { cp_async_wait<0>(); return; }
+    }
+    pipe.set_pose(a.pose_f32 + 12 * pair);
+  }
   cp_async_wait<0>();
   __syncthreads();
   pipe.sd = s_d; pipe.cl = warp * kChunksPerWarp;
@@ -696,6 +707,17 @@ k_icp_fused(const __grid_constant__ FusedArgs a) {
 template <int ROBUST, bool NGATE, bool WRITE_IDX, bool PHOTO, bool EARLY>
 static cudaError_t launch_icp_t(const IcpArgs& a, int n_pairs, cudaStream_t s) {
   dim3 grid(a.blocks_per_pair, n_pairs);
+  if (a.pdl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kIcpThreads, 1, 1);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_icp_iter<ROBUST, NGATE, WRITE_IDX, PHOTO, EARLY>, a);
+  }
   k_icp_iter<ROBUST, NGATE, WRITE_IDX, PHOTO, EARLY><<<grid, kIcpThreads, 0, s>>>(a);
   return cudaGetLastError();
 }

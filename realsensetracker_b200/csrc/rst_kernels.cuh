@@ -112,6 +112,7 @@ struct IcpArgs {
   float converge_eps;         // > 0: set done[pair] when an update is smaller than this
   uint8_t* done;              // [pair]: skip the rest of the level (nullptr when converge_eps == 0)
   int32_t update_pose;        // 0: evaluate only
+  int32_t pdl;                // launched with programmatic stream serialization: wait for the previous launch in-kernel
   int32_t* idx_out;           // WRITE_IDX: [pair-local][h*w]
 };
 

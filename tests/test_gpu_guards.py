@@ -108,3 +108,45 @@ def test_failed_coarse_level_does_not_fail_a_pair_that_converged():
         assert synth.pose_error(T[0], gt)[0] < 3e-3
     finally:
         al.close()
+
+
+def test_graph_replay_is_bit_identical_to_direct_launches(seq_small):
+    """Small blocking calls replay a CUDA graph of their kernels (the latency path). Same kernels, same arguments:
+    the results must be bit-identical to the direct launches, call after call, for sequences and pairs, and a
+    parameter change must re-capture rather than replay a stale graph."""
+    frames, gt, intr = seq_small
+    n, h, w = frames.shape
+    al = Aligner(w, h, 2 * n, n)
+    try:
+        for tiling in (0, 1):
+            P = default_params(tiling=tiling)
+            al.set_graph_max_pairs(0)
+            T_d, st_d = al.align_sequence(frames, intr, P)
+            Tp_d, _ = al.align_pairs(frames[1:3], frames[0:2], intr, P)
+            l0 = al.launch_count
+            al.align_sequence(frames, intr, P)
+            direct_launches = al.launch_count - l0
+            al.set_graph_max_pairs(8)
+            for _ in range(3):                                   # capture, then two replays
+                T_g, st_g = al.align_sequence(frames, intr, P)
+                assert np.array_equal(T_g, T_d)
+                assert [s.count for s in st_g] == [s.count for s in st_d] and all(s.status == 0 for s in st_g)
+            l0 = al.launch_count
+            al.align_sequence(frames, intr, P)
+            assert al.launch_count - l0 == direct_launches       # a replay accounts for the launches it contains
+            Tp_g, _ = al.align_pairs(frames[1:3], frames[0:2], intr, P)
+            assert np.array_equal(Tp_g, Tp_d)
+        P2 = default_params(iters=[3, 2, 1, 0])
+        al.set_graph_max_pairs(0)
+        T2_d, _ = al.align_sequence(frames, intr, P2)
+        al.set_graph_max_pairs(8)
+        T2_g, _ = al.align_sequence(frames, intr, P2)
+        assert np.array_equal(T2_g, T2_d) and not np.array_equal(T2_g, T_d)
+        T0 = np.stack([gt[i] for i in range(n - 1)])              # the initial pose is data, not part of the graph
+        al.set_graph_max_pairs(0)
+        T3_d, _ = al.align_sequence(frames, intr, P2, T0=T0)
+        al.set_graph_max_pairs(8)
+        T3_g, _ = al.align_sequence(frames, intr, P2, T0=T0)
+        assert np.array_equal(T3_g, T3_d) and not np.array_equal(T3_g, T2_g)
+    finally:
+        al.close()
