@@ -19,11 +19,11 @@ LIBDIR = PKG / "_lib"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "--shared", "-Xcompiler", "-fPIC",
-    "-cudart", "static",
+    "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
     "-I", str(ROOT / "include"),
 ]
+NVCC_LINK_FLAGS = ["--shared", "-Xcompiler", "-fPIC", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a"]
 
 # /opt/gcc/bin (the image's $CC) lacks libgomp.spec; the system compilers have it.
 HOST_CC = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
@@ -58,9 +58,24 @@ def build_align(force: bool = False) -> Path:
     LIBDIR.mkdir(exist_ok=True)
     out = LIBDIR / "librst_align.so"
     cu = sorted(CSRC.glob("*.cu"))
-    deps = cu + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [ROOT / "include" / "rst_align.h"]
+    deps = cu + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.inl")) + sorted(CSRC.glob("*.h")) + [ROOT / "include" / "rst_align.h"]
     if force or _stale(out, deps):
-        _run([_nvcc(), *NVCC_FLAGS, "-ccbin", HOST_CXX, "-o", str(out), *map(str, cu)], "nvcc_ptxas.log")
+        # one object per translation unit, compiled concurrently (no cross-file device calls), then one link
+        from concurrent.futures import ThreadPoolExecutor
+        objdir = LIBDIR / "obj"
+        objdir.mkdir(exist_ok=True)
+        hdrs = [d for d in deps if d not in cu]
+
+        def compile_one(src: Path) -> str:
+            obj = objdir / (src.stem + ".o")
+            if force or _stale(obj, [src, *hdrs]):
+                return _run([_nvcc(), *NVCC_FLAGS, "-ccbin", HOST_CXX, "-c", "-o", str(obj), str(src)])
+            return ""
+
+        with ThreadPoolExecutor(max_workers=len(cu)) as ex:
+            logs = list(ex.map(compile_one, cu))
+        (LIBDIR / "nvcc_ptxas.log").write_text("\n".join(logs))
+        _run([_nvcc(), *NVCC_LINK_FLAGS, "-ccbin", HOST_CXX, "-o", str(out), *[str(objdir / (c.stem + ".o")) for c in cu]])
     return out
 
 

@@ -367,6 +367,81 @@ __device__ __forceinline__ void stage_depth(uint32_t (*dst)[32], const uint16_t*
   cp_async_commit();
 }
 
+// Bulk-copy form of stage_depth (k_icp_iter): the tile is a run of consecutive chunks, i.e. a run of row segments, and
+// a row segment is contiguous both in global memory (up to the row pitch) and in the chunk-major tile. Warp 0 issues
+// ONE cp.async.bulk per row segment (one per lane, a single copy for the whole tile when rows are dense: w a multiple
+// of 64) that completes on `bar`; no per-16-byte address arithmetic, no LDGSTS issue slots. What a copy cannot deliver
+// is zero-filled with plain stores: the columns between the pitch and the end of a row's last chunk, and chunks below
+// the image. Every thread of the block calls this; after mbar_wait(bar, parity) + stage_depth_bulk_fix + a block
+// barrier the tile is complete.
+struct BulkTile {
+  int v0, n_rows, c_base, c_end;
+};
+__device__ __forceinline__ BulkTile stage_depth_bulk(uint32_t (*dst)[32], const uint16_t* __restrict__ Ds, int pitch, int H,
+                                                     int cpr, uint32_t cpr_magic, int c_base, int n_chunks, uint64_t* bar, int tid) {
+  BulkTile t;
+  t.c_base = c_base; t.c_end = c_base + n_chunks;
+  t.v0 = cpr == 1 ? c_base : (int)__umulhi((uint32_t)c_base, cpr_magic);
+  const int v_last = cpr == 1 ? t.c_end - 1 : (int)__umulhi((uint32_t)(t.c_end - 1), cpr_magic);
+  t.n_rows = v_last - t.v0 + 1;
+  uint16_t* d16 = reinterpret_cast<uint16_t*>(&dst[0][0]);
+  const int row_px = cpr * kChunkPx;
+  if (tid < 32) {
+    if (pitch == row_px) {   // dense rows: the whole tile is one contiguous run, clipped at the image end
+      if (tid == 0) {
+        const int c_img = H * cpr;
+        const int nc = min(t.c_end, c_img) - c_base;
+        const uint32_t bytes = nc > 0 ? (uint32_t)nc * (kChunkPx * 2) : 0u;
+        mbar_arrive_expect_tx(bar, bytes);
+        if (bytes) bulk_g2s(d16, Ds + (uint32_t)c_base * kChunkPx, bytes, bar);
+      }
+    } else {
+      uint32_t total = 0;
+      for (int r = tid; r < t.n_rows; r += 32) {
+        const int v = t.v0 + r, cr = v * cpr;
+        const int ca = max(c_base, cr) - cr, cb = min(t.c_end, cr + cpr) - cr;
+        const int px = min(cb * kChunkPx, pitch) - ca * kChunkPx;
+        if (v < H) total += (uint32_t)px * 2;
+      }
+      total = __reduce_add_sync(0xffffffffu, total);
+      if (tid == 0) mbar_arrive_expect_tx(bar, total);
+      __syncwarp();
+      for (int r = tid; r < t.n_rows; r += 32) {
+        const int v = t.v0 + r, cr = v * cpr;
+        const int ca = max(c_base, cr) - cr, cb = min(t.c_end, cr + cpr) - cr;
+        const int px = min(cb * kChunkPx, pitch) - ca * kChunkPx;
+        if (v < H) bulk_g2s(d16 + (cr + ca - c_base) * kChunkPx, Ds + (uint32_t)(v * pitch + ca * kChunkPx), (uint32_t)px * 2, bar);
+      }
+    }
+  }
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  if (pitch < row_px) {   // columns [pitch, row_px) of every row that ends inside the tile (block-uniform branch)
+    const int ppr = (row_px - pitch) >> 3;   // 16-byte pieces, 1..7
+    for (int r = tid >> 3; r < t.n_rows; r += kIcpThreads >> 3) {
+      const int v = t.v0 + r, cr = v * cpr, piece = tid & 7;
+      if (piece < ppr && v < H && cr + cpr <= t.c_end)
+        *reinterpret_cast<uint4*>(d16 + (cr - c_base) * kChunkPx + pitch + piece * 8) = z4;
+    }
+  }
+  {  // chunks below the image (last block of a pair only)
+    const int c_zero = max(c_base, H * cpr);
+    for (int q = (c_zero - c_base) * 8 + tid; q < n_chunks * 8; q += kIcpThreads)
+      *reinterpret_cast<uint4*>(d16 + q * 8) = z4;
+  }
+  return t;
+}
+// After the copies have landed: columns [w, pitch) hold whatever the caller's row padding holds (frames bound in place
+// with rst_set_frames_device); they count as invalid depth.
+__device__ __forceinline__ void stage_depth_bulk_fix(uint32_t (*dst)[32], const BulkTile& t, int pitch, int W, int H, int cpr, int tid) {
+  if (W >= pitch) return;
+  uint16_t* d16 = reinterpret_cast<uint16_t*>(&dst[0][0]);
+  for (int r = tid; r < t.n_rows; r += kIcpThreads) {
+    const int v = t.v0 + r, cr = v * cpr;
+    if (v < H && cr + cpr <= t.c_end)
+      for (int u = W; u < pitch; ++u) d16[(cr - t.c_base) * kChunkPx + u] = 0;
+  }
+}
+
 // K5 stage 1 inside a block: fixed-shape warp tree (xor 16,8,4,2,1, transposed), then the warps in index order.
 // Returns, for tid < kAcc, the block's sum of column tid (other threads: 0). Contains one __syncthreads.
 __device__ __forceinline__ float block_reduce29(const Accum29& a29, float (*s_warp)[kAccPad], int tid, int lane, int warp) {
@@ -471,10 +546,12 @@ k_icp_iter(const __grid_constant__ IcpArgs a) {
   __shared__ __align__(16) uint32_t s_d[kMaxGroups * kChunksPerBlock][32];
   __shared__ float s_warp[kIcpThreads / 32][kAccPad];
   __shared__ double s_tot[kAccPad];
+  __shared__ __align__(8) uint64_t s_bar;   // completion of the bulk copies of the depth tile
   __shared__ int s_last;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pair = a.pair_offset + blockIdx.y;
+  if (tid == 0) mbar_init(&s_bar, 1);       // warp 0 arms it below (same warp: program order), the others wait after the barrier
   if (EARLY && !a.pdl) {  // convergence test on: this pair may have left the level already (block-uniform)
     if (a.done[pair]) return;
   }
@@ -506,17 +583,36 @@ k_icp_iter(const __grid_constant__ IcpArgs a) {
     const int v = a.chunks_per_row == 1 ? c : (int)__umulhi((uint32_t)c, a.cpr_magic);  // c / chunks_per_row
     pipe.pos.v = v; pipe.pos.u = (c - v * a.chunks_per_row) * kChunkPx + lane;
   }
-  stage_depth(s_d, Ds, a.lv.depth_pitch, W, H, a.chunks_per_row, a.cpr_magic, blockIdx.x * a.groups * kChunksPerBlock,
-              a.groups * kChunksPerBlock, tid);
-  if (a.pdl) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (EARLY) {
-      if (a.done[pair]) { cp_async_wait<0>(); return; }
+  // Depth tile: bulk copies (one per row segment, a single one when rows are dense) unless the rows are short
+  // (coarse levels of ragged sizes), where 16-byte cp.async spread over all threads has less latency than a train of
+  // small bulk copies. Block-uniform choice.
+  const int c_base = blockIdx.x * a.groups * kChunksPerBlock;
+  if (a.lv.depth_pitch == a.chunks_per_row * kChunkPx || a.lv.depth_pitch >= 256) {
+    __syncwarp();
+    const BulkTile bt = stage_depth_bulk(s_d, Ds, a.lv.depth_pitch, H, a.chunks_per_row, a.cpr_magic, c_base,
+                                         a.groups * kChunksPerBlock, &s_bar, tid);
+    if (a.pdl) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      pipe.set_pose(a.pose_f32 + 12 * pair);
     }
-    pipe.set_pose(a.pose_f32 + 12 * pair);
+    __syncthreads();          // s_bar initialised for everyone; zero-fill stores visible
+    mbar_wait(&s_bar, 0);     // the tile has landed (nobody may leave before: the copies target this block's shared memory)
+    if (W < a.lv.depth_pitch) {
+      stage_depth_bulk_fix(s_d, bt, a.lv.depth_pitch, W, H, a.chunks_per_row, tid);
+      __syncthreads();
+    }
+  } else {
+    stage_depth(s_d, Ds, a.lv.depth_pitch, W, H, a.chunks_per_row, a.cpr_magic, c_base, a.groups * kChunksPerBlock, tid);
+    if (a.pdl) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      pipe.set_pose(a.pose_f32 + 12 * pair);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
   }
-  cp_async_wait<0>();
-  __syncthreads();
+  if (EARLY && a.pdl) {
+    if (a.done[pair]) return;
+  }
   pipe.sd = s_d; pipe.cl = warp * kChunksPerWarp;
   pipe.template run<0>(a.groups, s_g, [](int) {});
 
@@ -723,27 +819,11 @@ static cudaError_t launch_icp_t(const IcpArgs& a, int n_pairs, cudaStream_t s) {
 }
 
 template <int ROBUST, bool PHOTO>
-static cudaError_t launch_icp_r(const IcpArgs& a, int n_pairs, bool ngate, bool widx, cudaStream_t s) {
+cudaError_t launch_icp_r(const IcpArgs& a, int n_pairs, bool ngate, bool widx, cudaStream_t s) {
   const bool early = a.done != nullptr;  // the convergence test never runs together with the index dump (rst_evaluate)
   if (widx) return ngate ? launch_icp_t<ROBUST, true, true, PHOTO, false>(a, n_pairs, s) : launch_icp_t<ROBUST, false, true, PHOTO, false>(a, n_pairs, s);
   if (early) return ngate ? launch_icp_t<ROBUST, true, false, PHOTO, true>(a, n_pairs, s) : launch_icp_t<ROBUST, false, false, PHOTO, true>(a, n_pairs, s);
   return ngate ? launch_icp_t<ROBUST, true, false, PHOTO, false>(a, n_pairs, s) : launch_icp_t<ROBUST, false, false, PHOTO, false>(a, n_pairs, s);
-}
-
-template <bool PHOTO>
-static cudaError_t launch_icp_p(const IcpArgs& a, int n_pairs, int robust_kind, bool ngate, bool widx, cudaStream_t s) {
-  switch (robust_kind) {
-    case RST_ROBUST_HUBER: return launch_icp_r<RST_ROBUST_HUBER, PHOTO>(a, n_pairs, ngate, widx, s);
-    case RST_ROBUST_GEMAN_MCCLURE: return launch_icp_r<RST_ROBUST_GEMAN_MCCLURE, PHOTO>(a, n_pairs, ngate, widx, s);
-    default: return launch_icp_r<RST_ROBUST_NONE, PHOTO>(a, n_pairs, ngate, widx, s);
-  }
-}
-
-cudaError_t launch_icp_iter(const IcpArgs& a, int n_pairs, int robust_kind, bool normal_gate, bool write_idx, bool photo,
-                            cudaStream_t s) {
-  if (n_pairs <= 0) return cudaSuccess;
-  return photo ? launch_icp_p<true>(a, n_pairs, robust_kind, normal_gate, write_idx, s)
-               : launch_icp_p<false>(a, n_pairs, robust_kind, normal_gate, write_idx, s);
 }
 
 template <int ROBUST, bool NGATE, bool PHOTO>
@@ -770,9 +850,78 @@ static cudaError_t launch_fused_t(const FusedArgs& a, int n_pairs, int cluster, 
 }
 
 template <int ROBUST>
-static cudaError_t launch_fused_r(const FusedArgs& a, int n_pairs, int cluster, bool ngate, bool photo, cudaStream_t s) {
+cudaError_t launch_fused_r(const FusedArgs& a, int n_pairs, int cluster, bool ngate, bool photo, cudaStream_t s) {
   if (photo) return ngate ? launch_fused_t<ROBUST, true, true>(a, n_pairs, cluster, s) : launch_fused_t<ROBUST, false, true>(a, n_pairs, cluster, s);
   return ngate ? launch_fused_t<ROBUST, true, false>(a, n_pairs, cluster, s) : launch_fused_t<ROBUST, false, false>(a, n_pairs, cluster, s);
+}
+
+// ----------------------------------------------------------------------------------
+// This file is compiled once per RST_ICP_PART (rst_icp_part*.cu): every part instantiates one slice of the kernel
+// variants, so the slices build concurrently. Part 0 also holds the run-time dispatch.
+// ----------------------------------------------------------------------------------
+#define RST_DECL_ICP(R, P) template cudaError_t launch_icp_r<R, P>(const IcpArgs&, int, bool, bool, cudaStream_t)
+#define RST_DECL_FUSED(R) template cudaError_t launch_fused_r<R>(const FusedArgs&, int, int, bool, bool, cudaStream_t)
+#if RST_ICP_PART == 0
+RST_DECL_ICP(RST_ROBUST_NONE, false);
+#else
+extern RST_DECL_ICP(RST_ROBUST_NONE, false);
+#endif
+#if RST_ICP_PART == 1
+RST_DECL_ICP(RST_ROBUST_HUBER, false);
+#else
+extern RST_DECL_ICP(RST_ROBUST_HUBER, false);
+#endif
+#if RST_ICP_PART == 2
+RST_DECL_ICP(RST_ROBUST_GEMAN_MCCLURE, false);
+#else
+extern RST_DECL_ICP(RST_ROBUST_GEMAN_MCCLURE, false);
+#endif
+#if RST_ICP_PART == 3
+RST_DECL_ICP(RST_ROBUST_NONE, true);
+#else
+extern RST_DECL_ICP(RST_ROBUST_NONE, true);
+#endif
+#if RST_ICP_PART == 4
+RST_DECL_ICP(RST_ROBUST_HUBER, true);
+#else
+extern RST_DECL_ICP(RST_ROBUST_HUBER, true);
+#endif
+#if RST_ICP_PART == 5
+RST_DECL_ICP(RST_ROBUST_GEMAN_MCCLURE, true);
+#else
+extern RST_DECL_ICP(RST_ROBUST_GEMAN_MCCLURE, true);
+#endif
+#if RST_ICP_PART == 6
+RST_DECL_FUSED(RST_ROBUST_NONE);
+#else
+extern RST_DECL_FUSED(RST_ROBUST_NONE);
+#endif
+#if RST_ICP_PART == 7
+RST_DECL_FUSED(RST_ROBUST_HUBER);
+#else
+extern RST_DECL_FUSED(RST_ROBUST_HUBER);
+#endif
+#if RST_ICP_PART == 8
+RST_DECL_FUSED(RST_ROBUST_GEMAN_MCCLURE);
+#else
+extern RST_DECL_FUSED(RST_ROBUST_GEMAN_MCCLURE);
+#endif
+
+#if RST_ICP_PART == 0
+template <bool PHOTO>
+static cudaError_t launch_icp_p(const IcpArgs& a, int n_pairs, int robust_kind, bool ngate, bool widx, cudaStream_t s) {
+  switch (robust_kind) {
+    case RST_ROBUST_HUBER: return launch_icp_r<RST_ROBUST_HUBER, PHOTO>(a, n_pairs, ngate, widx, s);
+    case RST_ROBUST_GEMAN_MCCLURE: return launch_icp_r<RST_ROBUST_GEMAN_MCCLURE, PHOTO>(a, n_pairs, ngate, widx, s);
+    default: return launch_icp_r<RST_ROBUST_NONE, PHOTO>(a, n_pairs, ngate, widx, s);
+  }
+}
+
+cudaError_t launch_icp_iter(const IcpArgs& a, int n_pairs, int robust_kind, bool normal_gate, bool write_idx, bool photo,
+                            cudaStream_t s) {
+  if (n_pairs <= 0) return cudaSuccess;
+  return photo ? launch_icp_p<true>(a, n_pairs, robust_kind, normal_gate, write_idx, s)
+               : launch_icp_p<false>(a, n_pairs, robust_kind, normal_gate, write_idx, s);
 }
 
 cudaError_t launch_icp_fused(const FusedArgs& a, int n_pairs, int cluster, int robust_kind, bool normal_gate, bool photo,
@@ -785,6 +934,9 @@ cudaError_t launch_icp_fused(const FusedArgs& a, int n_pairs, int cluster, int r
   }
 }
 
+#endif  // part 0
+
+#if RST_ICP_PART == 6
 // how many clusters of `cluster` CTAs of the plain fused kernel the device can hold at once (0 on error)
 int fused_max_active_clusters(int cluster) {
   auto kern = k_icp_fused<RST_ROBUST_NONE, false, false>;
@@ -803,5 +955,7 @@ int fused_max_active_clusters(int cluster) {
   if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
+
+#endif  // part 6
 
 }  // namespace rst

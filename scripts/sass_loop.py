@@ -3,7 +3,7 @@
 
   python scripts/sass_loop.py [--fn SUBSTR] [--px N] [-- extra nvcc flags]
 
-Compiles realsensetracker_b200/csrc/rst_kernels.cu to a cubin (sm_100a), dumps the SASS of the first
+Compiles realsensetracker_b200/csrc/rst_icp_part0_iter_plain.cu to a cubin (sm_100a), dumps the SASS of the first
 function whose demangled name contains SUBSTR (default: the plain level-0 ICP kernel), takes the backward-branch
 region with the most FFMA/FFMA2/LDGSTS as "the loop" and prints instructions per pixel by opcode (--px = pixels one
 thread handles per loop trip; k_icp_iter: 2 stages x 2*CPW pixels = 8).
@@ -21,9 +21,9 @@ ROOT = Path(__file__).resolve().parent.parent
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--fn", default="k_icp_iter<0, false, false, false, false>")
+    ap.add_argument("--fn", default="k_icp_iter<(int)0, (bool)0, (bool)0, (bool)0, (bool)0>")
     ap.add_argument("--px", type=float, default=8.0)
-    ap.add_argument("--src", default="realsensetracker_b200/csrc/rst_kernels.cu")
+    ap.add_argument("--src", default="realsensetracker_b200/csrc/rst_icp_part0_iter_plain.cu")
     ap.add_argument("--dump", default=None, help="write the function's SASS here")
     ap.add_argument("rest", nargs="*")
     a = ap.parse_args()
