@@ -565,7 +565,18 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                 okr, Tr, mcr, cnts = al.icp3d_depth(frames, sidx, didx, intr)
             dtr = (time.perf_counter() - t0r) / reps
             rerr = np.array([synth.pose_error(Tr[i], gt[i]) for i in range(n_pairs)])
-            ref_gpu = {"value": n_pairs / dtr, "unit": "pairs/s", "ms_per_step": dtr * 1e3, "timing": "host wall clock, H2D + D2H included",
+            # one pair at a time, as the reference's caller runs it (rs_replay_app.cpp:246-251): one CTA per pair vs the
+            # automatic thread-block cluster per pair
+            single = {}
+            for name, ctas in (("one_cta_per_pair", 1), ("cluster_per_pair", 0)):
+                al.set_icp3d_cluster(ctas)
+                al.icp3d_depth(frames[:2], sidx[:1], didx[:1], intr)
+                t0s = time.perf_counter()
+                for _ in range(10):
+                    al.icp3d_depth(frames[:2], sidx[:1], didx[:1], intr)
+                single[name + "_ms"] = (time.perf_counter() - t0s) / 10 * 1e3
+            al.set_icp3d_cluster(0)
+            ref_gpu = {"value": n_pairs / dtr, "single_pair": single, "unit": "pairs/s", "ms_per_step": dtr * 1e3, "timing": "host wall clock, H2D + D2H included",
                        "algorithm": "reference AlignIcp3d on the GPU: exact grid NN, GM/GNC weights, Kabsch, 128 iterations, voxel 0.05",
                        "mean_cloud_points": float(np.mean(cnts)), "pairs_ok": int(okr.sum()),
                        "pose_err_vs_gt": {"t_m_max": float(rerr[:, 0].max()), "r_rad_max": float(rerr[:, 1].max())}}

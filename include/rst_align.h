@@ -337,6 +337,13 @@ int32_t rst_icp3d_pairs(rst_ctx* ctx, const rst_cloud* src, const rst_cloud* dst
                         int32_t max_iter, float grid_cell, float* poses_inout,
                         rst_icp3d_result* results, int32_t* nbrs_out, float* weights_out);
 
+/* CTAs per pair of the cloud ICP kernel (rst_icp3d_pairs / rst_icp3d_depth): 0 (default) = automatic — one CTA per
+ * pair for batches that fill the GPU, a thread-block cluster of up to 16 CTAs per pair for small batches (a single
+ * pair, the reference caller's case, then runs on 16 SMs instead of one); 1, 2, 4, 8, 16 force a size. Results of
+ * different sizes agree to fp64 round-off of the partial-sum order (neighbour indices: bit-identical for the same
+ * pose). */
+int32_t rst_set_icp3d_cluster(rst_ctx* ctx, int32_t ctas_per_pair);
+
 /* bool SolveKabsch(src, dst, indices, weights, &xfm)  (align_icp.hpp:14-18, align_icp.cpp:18-71) on the device:
  * closed-form pose from GIVEN (src index, dst index) pairs — the initialiser rs_align_app.cpp:295 feeds to
  * AlignIcp3d. `pairs`: n_pairs x 2 int32; `weights`: n_pairs floats or NULL (the reference's empty vector);

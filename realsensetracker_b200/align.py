@@ -336,6 +336,10 @@ class Aligner:
         """Blocking host-frame calls with at most this many pairs replay a CUDA graph (default 8; 0 = never)."""
         self._check(self._lib.rst_set_graph_max_pairs(self._ctx, max_pairs))
 
+    def set_icp3d_cluster(self, ctas_per_pair: int):
+        """CTAs per pair of the cloud ICP kernel: 0 = automatic, or 1 / 2 / 4 / 8 / 16."""
+        self._check(self._lib.rst_set_icp3d_cluster(self._ctx, ctas_per_pair))
+
     def set_schedule(self, schedule: int):
         """0 = fused (one cluster per pair, all iterations in one launch; default), 1 = one launch per iteration."""
         self._check(self._lib.rst_set_schedule(self._ctx, schedule))

@@ -164,3 +164,32 @@ def test_cloud_normals_on_the_device(al):
         assert np.median(cosang) > 0.99999 and (cosang > 0.999).mean() > 0.97   # near-isotropic neighbourhoods may differ
         assert ((gpu * cloud).sum(1) <= 1e-6).all()
         assert ((ref * gpu).sum(1) > 0).mean() > 0.97                      # same orientation
+
+
+def test_cluster_per_pair_agrees_with_one_cta_per_pair(al):
+    """Small batches run a thread-block cluster per pair (the source points split over its CTAs, sums through
+    distributed shared memory). Same neighbours bit for bit after one iteration from the same pose; the 128-iteration
+    pose within fp64 partial-sum round-off of the one-CTA result; a two-pair batch, ragged cloud sizes and a
+    degenerate pair (fewer than 3 points) take the same path."""
+    src, dst = depth_clouds(1, 0)
+    src2, dst2 = GOLD["src"], GOLD["dst"]
+    try:
+        al.set_icp3d_cluster(1)
+        ok1, T1, ex1 = al.icp3d_pairs([src, src2], [dst, dst2], 1, details=True)
+        okf, Tf, exf = al.icp3d_pairs([src, src2], [dst, dst2], 128, details=True)
+        for c in (2, 8, 16, 0):
+            al.set_icp3d_cluster(c)
+            ok_c, T_c, ex_c = al.icp3d_pairs([src, src2], [dst, dst2], 1, details=True)
+            for i in range(2):
+                assert np.array_equal(ex_c[i]["nbrs"], ex1[i]["nbrs"]) and np.array_equal(ex_c[i]["weights"], ex1[i]["weights"])
+                assert np.allclose(ex_c[i]["cov"], ex1[i]["cov"], rtol=1e-12, atol=1e-12 * np.abs(ex1[i]["cov"]).max())
+            ok_c, T_c, ex_c = al.icp3d_pairs([src, src2], [dst, dst2], 128, details=True)
+            for i in range(2):
+                dt, dr = synth.pose_error(T_c[i], Tf[i])
+                assert ok_c[i] == okf[i] and dt < 1e-5 and dr < 1e-5, (c, i, dt, dr)
+                assert abs(ex_c[i]["mean_cost"] - exf[i]["mean_cost"]) <= 1e-5 * max(exf[i]["mean_cost"], 1e-6)
+        al.set_icp3d_cluster(16)
+        ok_d, T_d = al.icp3d_pairs([src[:2]], [dst], 8, T0=np.eye(4))   # fewer than 3 points: false, pose untouched
+        assert not ok_d[0] and np.array_equal(T_d[0], np.eye(4, dtype=np.float32))
+    finally:
+        al.set_icp3d_cluster(0)
