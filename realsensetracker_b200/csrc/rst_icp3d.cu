@@ -129,23 +129,34 @@ __device__ Grid build_grid(const float* __restrict__ pts, int n, float grid_cell
   __syncthreads();
   for (int j = tid; j < n; j += kThreads) atomicAdd(cell_fill + cell_of(j), 1);
   __syncthreads();
-  {
-    const int per = (n_cells + kThreads - 1) / kThreads;
-    const int c0 = tid * per, c1 = min(c0 + per, n_cells);
-    int local = 0;
-    for (int c = c0; c < c1; ++c) local += cell_fill[c];
-    int incl = local;  // inclusive scan of the per-thread totals
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-    if (lane == 31) s_scan[warp] = incl;
+  {  // exclusive scan of the cell counts in coalesced tiles of 4 cells per thread; cell_fill is reset on the way
+    __shared__ int s_carry;
+    if (tid == 0) s_carry = 0;
     __syncthreads();
-    if (warp == 0) {
-      int v = s_scan[lane];
-      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-      s_scan[lane] = v;
+    for (int base = 0; base < n_cells; base += 4 * kThreads) {
+      const int c = base + 4 * tid;
+      int k4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) k4[q] = c + q < n_cells ? cell_fill[c + q] : 0;
+      const int local = k4[0] + k4[1] + k4[2] + k4[3];
+      int incl = local;
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      if (lane == 31) s_scan[warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        int v = s_scan[lane];
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+        s_scan[lane] = v;
+      }
+      __syncthreads();
+      int run = s_carry + incl - local + (warp > 0 ? s_scan[warp - 1] : 0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (c + q < n_cells) { cell_start[c + q] = run; cell_fill[c + q] = 0; run += k4[q]; }
+      __syncthreads();
+      if (tid == kThreads - 1) s_carry = run;
+      __syncthreads();
     }
-    __syncthreads();
-    int run = incl - local + (warp > 0 ? s_scan[warp - 1] : 0);
-    for (int c = c0; c < c1; ++c) { const int k = cell_fill[c]; cell_start[c] = run; cell_fill[c] = 0; run += k; }
     if (tid == 0) cell_start[n_cells] = n;
   }
   __syncthreads();
@@ -511,9 +522,9 @@ cudaError_t launch_icp3d(const PairDesc* descs, int n_pairs, int max_iter, float
 // (point_cloud_utils.cpp:163-174; nothing to drop: the back-projection emits no NaN) and
 // DownsampleVoxel (point_cloud_utils.cpp:34-68): key = floor(p / voxel), the FIRST point of a voxel
 // wins. The reference's output order is unordered_map iteration order (implementation-defined);
-// here it is first-occurrence order, which is deterministic. One 1024-thread block per frame:
-// pass 1 inserts atomicMin(pixel index) per voxel into an open-addressing hash table, pass 2 keeps
-// the winners with an order-preserving block scan.
+// here it is first-occurrence order, which is deterministic. Pass 1 inserts atomicMin(pixel index) per
+// voxel into an open-addressing hash table, pass 2 keeps the winners in pixel order (segment counts,
+// scan, order-preserving write).
 // ----------------------------------------------------------------------------------------------
 struct CloudifyDesc {
   const uint16_t* depth;           // dense w*h
@@ -521,6 +532,7 @@ struct CloudifyDesc {
   int* vals;                       // [cap]
   float* cloud;                    // out, up to w*h points
   int* count;                      // out
+  int* seg;                        // [ceil(w*h / kSegPx)] winners per pixel segment, then their exclusive scan
 };
 
 constexpr unsigned long long kEmptyKey = 0ull;
@@ -549,42 +561,81 @@ __device__ __forceinline__ uint32_t hash_key(unsigned long long k) {
   return (uint32_t)k;
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_cloudify(const CloudifyDesc* __restrict__ descs, int w, int h, float fx, float fy,
-                                                          float cx, float cy, float scale, float voxel, uint32_t cap_mask) {
-  __shared__ int s_scan[kWarps];
-  __shared__ int s_base;
-  const CloudifyDesc D = descs[blockIdx.x];
+// Four launches, every one over as many blocks as the frames need (a single frame uses the whole GPU):
+//   k_cloudify_insert : one thread per pixel, atomicMin(pixel index) per voxel in the frame's hash table
+//   k_cloudify_count  : winners per segment of kSegPx consecutive pixels
+//   k_cloudify_scan   : exclusive scan of the segment counts of a frame (one block per frame), point count out
+//   k_cloudify_write  : winners of a segment, in pixel order, at the segment's offset
+constexpr int kSegThreads = 256, kSegPerThread = 8, kSegPx = kSegThreads * kSegPerThread;
+
+__global__ void __launch_bounds__(256) k_cloudify_insert(const CloudifyDesc* __restrict__ descs, int w, int h, float fx, float fy,
+                                                         float cx, float cy, float scale, float voxel, uint32_t cap_mask) {
+  const CloudifyDesc D = descs[blockIdx.y];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= w * h) return;
+  float p[3];
+  backproject_px(D.depth, i, w, fx, fy, cx, cy, scale, p);
+  const unsigned long long key = voxel_key(p, voxel);
+  uint32_t slot = hash_key(key) & cap_mask;
+  for (;;) {
+    const unsigned long long prev = atomicCAS(D.keys + slot, kEmptyKey, key);
+    if (prev == kEmptyKey || prev == key) { atomicMin(D.vals + slot, i); break; }
+    slot = (slot + 1) & cap_mask;
+  }
+}
+
+__device__ __forceinline__ bool cloudify_winner(const CloudifyDesc& D, int i, int w, float fx, float fy, float cx, float cy, float scale,
+                                                float voxel, uint32_t cap_mask, float* p) {
+  backproject_px(D.depth, i, w, fx, fy, cx, cy, scale, p);
+  if (!(voxel > 0.f)) return true;
+  const unsigned long long key = voxel_key(p, voxel);
+  uint32_t slot = hash_key(key) & cap_mask;
+  while (D.keys[slot] != key) slot = (slot + 1) & cap_mask;
+  return D.vals[slot] == i;
+}
+
+// WRITE = false: seg[blockIdx.x] = winners of this segment. WRITE = true: seg[] holds the exclusive scan; the winners
+// are written in pixel order (order-preserving compaction: contiguous run per thread, block scan of the run counts).
+template <bool WRITE>
+__global__ void __launch_bounds__(kSegThreads) k_cloudify_segment(const CloudifyDesc* __restrict__ descs, int w, int h, float fx, float fy,
+                                                                   float cx, float cy, float scale, float voxel, uint32_t cap_mask) {
+  __shared__ int s_scan[kSegThreads / 32];
+  const CloudifyDesc D = descs[blockIdx.y];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = w * h;
-  const bool decimate = voxel > 0.f;
-  if (decimate) {
-    for (int i = tid; i < n; i += kThreads) {
-      float p[3];
-      backproject_px(D.depth, i, w, fx, fy, cx, cy, scale, p);
-      const unsigned long long key = voxel_key(p, voxel);
-      uint32_t slot = hash_key(key) & cap_mask;
-      for (;;) {
-        const unsigned long long prev = atomicCAS(D.keys + slot, kEmptyKey, key);
-        if (prev == kEmptyKey || prev == key) { atomicMin(D.vals + slot, i); break; }
-        slot = (slot + 1) & cap_mask;
-      }
-    }
-    __syncthreads();
-  }
-  // order-preserving compaction: contiguous segment per thread, exclusive scan of the winner counts
-  const int per = (n + kThreads - 1) / kThreads;
-  const int i0 = tid * per, i1 = min(i0 + per, n);
-  auto is_winner = [&](int i, float* p) -> bool {
-    backproject_px(D.depth, i, w, fx, fy, cx, cy, scale, p);
-    if (!decimate) return true;
-    const unsigned long long key = voxel_key(p, voxel);
-    uint32_t slot = hash_key(key) & cap_mask;
-    while (D.keys[slot] != key) slot = (slot + 1) & cap_mask;
-    return D.vals[slot] == i;
-  };
-  int local = 0;
+  const int i0 = min(blockIdx.x * kSegPx + tid * kSegPerThread, n), i1 = min(i0 + kSegPerThread, n);
   float p[3];
-  for (int i = i0; i < i1; ++i) local += is_winner(i, p) ? 1 : 0;
+  uint32_t win = 0;
+  for (int i = i0; i < i1; ++i) win |= (cloudify_winner(D, i, w, fx, fy, cx, cy, scale, voxel, cap_mask, p) ? 1u : 0u) << (i - i0);
+  const int local = __popc(win);
+  int incl = local;
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) s_scan[warp] = incl;
+  __syncthreads();
+  int base = 0;
+  for (int k = 0; k < warp; ++k) base += s_scan[k];
+  if (!WRITE) {
+    if (tid == kSegThreads - 1) D.seg[blockIdx.x] = base + incl;
+    return;
+  }
+  int pos = D.seg[blockIdx.x] + base + incl - local;
+  for (int i = i0; i < i1; ++i)
+    if ((win >> (i - i0)) & 1u) {
+      backproject_px(D.depth, i, w, fx, fy, cx, cy, scale, p);
+      D.cloud[3 * pos] = p[0]; D.cloud[3 * pos + 1] = p[1]; D.cloud[3 * pos + 2] = p[2];
+      ++pos;
+    }
+}
+
+// exclusive scan of a frame's segment counts in place; the total is the frame's point count
+__global__ void __launch_bounds__(kThreads) k_cloudify_scan(const CloudifyDesc* __restrict__ descs, int n_seg) {
+  __shared__ int s_scan[kWarps];
+  const CloudifyDesc D = descs[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (n_seg + kThreads - 1) / kThreads;
+  const int k0 = min(tid * per, n_seg), k1 = min(k0 + per, n_seg);
+  int local = 0;
+  for (int k = k0; k < k1; ++k) local += D.seg[k];
   int incl = local;
   for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
   if (lane == 31) s_scan[warp] = incl;
@@ -595,11 +646,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_cloudify(const CloudifyDesc* __
     s_scan[lane] = v;
   }
   __syncthreads();
-  int pos = incl - local + (warp > 0 ? s_scan[warp - 1] : 0);
-  for (int i = i0; i < i1; ++i)
-    if (is_winner(i, p)) { D.cloud[3 * pos] = p[0]; D.cloud[3 * pos + 1] = p[1]; D.cloud[3 * pos + 2] = p[2]; ++pos; }
-  if (tid == kThreads - 1) *D.count = incl - local + (warp > 0 ? s_scan[warp - 1] : 0) + local;
-  (void)s_base;
+  int run = incl - local + (warp > 0 ? s_scan[warp - 1] : 0);
+  for (int k = k0; k < k1; ++k) { const int c = D.seg[k]; D.seg[k] = run; run += c; }
+  if (tid == kThreads - 1) *D.count = run;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -653,16 +702,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_kabsch(const float* __restrict_
 // exact k nearest neighbours (k includes the point itself, :184), fp32 centroid and covariance summed
 // in ascending-distance order (:187-198), eigenvector of the smallest eigenvalue of the 3x3 covariance
 // (SelfAdjointEigenSolver, :201-202; here a cyclic Jacobi in fp32), flipped so that
-// n . (p - viewpoint) <= 0 (:210-214). One block per cloud: the grid of the cloud is built exactly as
-// for the ICP, then each thread owns points tid, tid + 1024, ...
+// n . (p - viewpoint) <= 0 (:210-214). The grid of the cloud is built exactly as for the ICP (one block,
+// k_grid_build), then one thread per point over as many blocks as the cloud needs.
 // ----------------------------------------------------------------------------------------------
+__global__ void k_grid_build(const float* __restrict__ pts, int n, float grid_cell, int* cell_start, int* cell_fill, float4* sorted,
+                             struct Grid* out);
 constexpr int kMaxK = 33;   // ComputeCovariances asks for 32 neighbours + the point itself
-
-struct NormalsDesc {
-  const float* pts; int n;
-  int* cell_start; int* cell_fill; float4* sorted;
-  float* normals;   // n x 3 out
-};
 
 // k nearest neighbours of p by ring expansion; (d2, index) kept sorted ascending, ties to the lower index
 __device__ void knn_search(const Grid& g, const int* __restrict__ cell_start, const float4* __restrict__ sorted, float px, float py,
@@ -733,31 +778,29 @@ __device__ void smallest_eigenvector(const float* C, float* out) {
   out[0] = v[m]; out[1] = v[3 + m]; out[2] = v[6 + m];
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_normals(const NormalsDesc* __restrict__ descs, int k, float grid_cell, float vx, float vy, float vz) {
-  const NormalsDesc P = descs[blockIdx.x];
-  const int tid = threadIdx.x;
-  if (P.n < 1) return;
-  const Grid g = build_grid(P.pts, P.n, grid_cell, P.cell_start, P.cell_fill, P.sorted);
-
-  for (int i = tid; i < P.n; i += kThreads) {
-    const float px = P.pts[3 * i], py = P.pts[3 * i + 1], pz = P.pts[3 * i + 2];
-    float bd[kMaxK]; int bj[kMaxK];
-    knn_search(g, P.cell_start, P.sorted, px, py, pz, k, bd, bj);
-    float cen[3] = {0.f, 0.f, 0.f};
-    for (int q = 0; q < k; ++q) for (int a = 0; a < 3; ++a) cen[a] += P.pts[3 * bj[q] + a];   // :188-191
-    for (int a = 0; a < 3; ++a) cen[a] /= (float)k;
-    float C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int q = 0; q < k; ++q) {                                                              // :194-198
-      float d[3];
-      for (int a = 0; a < 3; ++a) d[a] = P.pts[3 * bj[q] + a] - cen[a];
-      for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) C[3 * a + b] += d[a] * d[b];
-    }
-    float nv[3];
-    smallest_eigenvector(C, nv);                                                               // :201-202
-    const float ray = (px - vx) * nv[0] + (py - vy) * nv[1] + (pz - vz) * nv[2];              // :209-213
-    const float sgn = ray > 0.f ? -1.f : 1.f;
-    for (int a = 0; a < 3; ++a) P.normals[3 * i + a] = sgn * nv[a];
+__global__ void __launch_bounds__(128) k_normals(const Grid* __restrict__ gp, const int* __restrict__ cell_start,
+                                                 const float4* __restrict__ sorted, const float* __restrict__ pts, int n, int k,
+                                                 float vx, float vy, float vz, float* __restrict__ normals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Grid g = *gp;
+  const float px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
+  float bd[kMaxK]; int bj[kMaxK];
+  knn_search(g, cell_start, sorted, px, py, pz, k, bd, bj);
+  float cen[3] = {0.f, 0.f, 0.f};
+  for (int q = 0; q < k; ++q) for (int a = 0; a < 3; ++a) cen[a] += pts[3 * bj[q] + a];   // :188-191
+  for (int a = 0; a < 3; ++a) cen[a] /= (float)k;
+  float C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int q = 0; q < k; ++q) {                                                            // :194-198
+    float d[3];
+    for (int a = 0; a < 3; ++a) d[a] = pts[3 * bj[q] + a] - cen[a];
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) C[3 * a + b] += d[a] * d[b];
   }
+  float nv[3];
+  smallest_eigenvector(C, nv);                                                             // :201-202
+  const float ray = (px - vx) * nv[0] + (py - vy) * nv[1] + (pz - vz) * nv[2];            // :209-213
+  const float sgn = ray > 0.f ? -1.f : 1.f;
+  for (int a = 0; a < 3; ++a) normals[3 * i + a] = sgn * nv[a];
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1240,6 +1283,8 @@ extern "C" int32_t rst_icp3d_depth(rst_ctx* c, const rst_frame* frames, int32_t 
   const size_t o_cloud = off; off = align_up(off + npx * 12 * n_frames);
   const size_t o_keys = off; off = align_up(off + (decimate ? (size_t)cap * 8 * n_frames : 0));
   const size_t o_vals = off; off = align_up(off + (decimate ? (size_t)cap * 4 * n_frames : 0));
+  const int n_seg = (int)((npx + kSegPx - 1) / kSegPx);
+  const size_t o_seg = off; off = align_up(off + sizeof(int) * (size_t)n_seg * n_frames);
   std::vector<size_t> o_cs(n_pairs), o_cf(n_pairs), o_sorted(n_pairs), o_nbr(n_pairs), o_w(n_pairs);
   for (int i = 0; i < n_pairs; ++i) {
     o_cs[i] = off; off = align_up(off + sizeof(int) * (kCellCap + 1));
@@ -1271,6 +1316,7 @@ extern "C" int32_t rst_icp3d_depth(rst_ctx* c, const rst_frame* frames, int32_t 
     cd[f].vals = reinterpret_cast<int*>(D + o_vals + (size_t)cap * 4 * f);
     cd[f].cloud = reinterpret_cast<float*>(D + o_cloud + npx * 12 * f);
     cd[f].count = reinterpret_cast<int*>(D + o_cnt) + f;
+    cd[f].seg = reinterpret_cast<int*>(D + o_seg) + (size_t)n_seg * f;
   }
   PairDesc* pd = reinterpret_cast<PairDesc*>(H + o_pdesc);
   for (int i = 0; i < n_pairs; ++i) {
@@ -1294,10 +1340,16 @@ extern "C" int32_t rst_icp3d_depth(rst_ctx* c, const rst_frame* frames, int32_t 
     ICP_CUDA(cudaMemsetAsync(D + o_vals, 0x7f, (size_t)cap * 4 * n_frames, stream));  // 0x7f7f7f7f > any pixel index
   }
   ICP_CUDA(cudaMemsetAsync(D + o_res, 0, sizeof(rst_icp3d_result) * (size_t)(n_pairs > 0 ? n_pairs : 1), stream));
-  k_cloudify<<<n_frames, kThreads, 0, stream>>>(reinterpret_cast<const CloudifyDesc*>(D + o_cdesc), w, h, intr->fx, intr->fy, intr->cx,
-                                                intr->cy, depth_scale, voxel, cap - 1);
-  ICP_CUDA(cudaGetLastError());
-  rst::ctx_count_launches(c, 1);
+  {
+    const CloudifyDesc* dd = reinterpret_cast<const CloudifyDesc*>(D + o_cdesc);
+    const dim3 gpx((unsigned)((npx + 255) / 256), n_frames), gseg(n_seg, n_frames);
+    if (decimate) k_cloudify_insert<<<gpx, 256, 0, stream>>>(dd, w, h, intr->fx, intr->fy, intr->cx, intr->cy, depth_scale, voxel, cap - 1);
+    k_cloudify_segment<false><<<gseg, kSegThreads, 0, stream>>>(dd, w, h, intr->fx, intr->fy, intr->cx, intr->cy, depth_scale, voxel, cap - 1);
+    k_cloudify_scan<<<n_frames, kThreads, 0, stream>>>(dd, n_seg);
+    k_cloudify_segment<true><<<gseg, kSegThreads, 0, stream>>>(dd, w, h, intr->fx, intr->fy, intr->cx, intr->cy, depth_scale, voxel, cap - 1);
+    ICP_CUDA(cudaGetLastError());
+    rst::ctx_count_launches(c, decimate ? 4 : 3);
+  }
   if (n_pairs > 0) {
     ICP_CUDA(launch_icp3d(reinterpret_cast<const PairDesc*>(D + o_pdesc), n_pairs, max_iter, grid_cell, st->icp3d_cluster, stream));
     rst::ctx_count_launches(c, 1);
@@ -1417,11 +1469,11 @@ extern "C" int32_t rst_cloud_normals(rst_ctx* c, const rst_cloud* cloud, int32_t
   st->last_frames = 0;
   const size_t n = (size_t)cloud->n;
   size_t off = 0;
-  const size_t o_desc = off; off = align_up(off + sizeof(NormalsDesc));
   const size_t o_pts = off; off = align_up(off + sizeof(float) * 3 * n);
   const size_t upload = off;
   const size_t o_nrm = off; off = align_up(off + sizeof(float) * 3 * n);
   const size_t host_end = off;
+  const size_t o_grid = off; off = align_up(off + sizeof(Grid));
   const size_t o_cs = off; off = align_up(off + sizeof(int) * (kCellCap + 1));
   const size_t o_cf = off; off = align_up(off + sizeof(int) * kCellCap);
   const size_t o_sorted = off; off = align_up(off + sizeof(float4) * n);
@@ -1440,16 +1492,17 @@ extern "C" int32_t rst_cloud_normals(rst_ctx* c, const rst_cloud* cloud, int32_t
   }
   char* H = static_cast<char*>(st->h_arena);
   char* D = static_cast<char*>(st->d_arena);
-  NormalsDesc d;
-  d.pts = reinterpret_cast<const float*>(D + o_pts); d.n = cloud->n;
-  d.cell_start = reinterpret_cast<int*>(D + o_cs); d.cell_fill = reinterpret_cast<int*>(D + o_cf);
-  d.sorted = reinterpret_cast<float4*>(D + o_sorted); d.normals = reinterpret_cast<float*>(D + o_nrm);
-  std::memcpy(H + o_desc, &d, sizeof(d));
   std::memcpy(H + o_pts, cloud->xyz, sizeof(float) * 3 * n);
   ICP_CUDA(cudaMemcpyAsync(D, H, upload, cudaMemcpyHostToDevice, stream));
-  k_normals<<<1, kThreads, 0, stream>>>(reinterpret_cast<const NormalsDesc*>(D + o_desc), k, grid_cell, viewpoint[0], viewpoint[1], viewpoint[2]);
+  k_grid_build<<<1, kThreads, 0, stream>>>(reinterpret_cast<const float*>(D + o_pts), (int)n, grid_cell, reinterpret_cast<int*>(D + o_cs),
+                                           reinterpret_cast<int*>(D + o_cf), reinterpret_cast<float4*>(D + o_sorted),
+                                           reinterpret_cast<Grid*>(D + o_grid));
+  k_normals<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(reinterpret_cast<const Grid*>(D + o_grid), reinterpret_cast<const int*>(D + o_cs),
+                                                             reinterpret_cast<const float4*>(D + o_sorted),
+                                                             reinterpret_cast<const float*>(D + o_pts), (int)n, k, viewpoint[0],
+                                                             viewpoint[1], viewpoint[2], reinterpret_cast<float*>(D + o_nrm));
   ICP_CUDA(cudaGetLastError());
-  rst::ctx_count_launches(c, 1);
+  rst::ctx_count_launches(c, 2);
   ICP_CUDA(cudaMemcpyAsync(H + o_nrm, D + o_nrm, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, stream));
   ICP_CUDA(cudaStreamSynchronize(stream));
   std::memcpy(normals_out, H + o_nrm, sizeof(float) * 3 * n);
