@@ -16,6 +16,8 @@
 
 #include "rst_align.h"
 #include "rst_internal.h"
+#include <cuda.h>   // CUtensorMap + the cuTensorMapEncodeTiled prototype (resolved at run time, libcuda is not linked)
+
 #include "rst_kernels.cuh"
 
 using namespace rst;
@@ -54,6 +56,8 @@ struct rst_ctx {
   int ext_pitch0 = 0;
   int64_t ext_frame0 = 0;
   int ext_first = 0, ext_count = 0;     // slots [ext_first, ext_first + ext_count) are backed by the caller's memory
+  TensorMap tmap[RST_MAX_LEVELS]{};     // (w, h, frames) uint16 view of every depth level for k_preprocess' TMA box
+  TensorMap tmap_ext0{};                // the same for level 0 bound in place (frame 0 = slot ext_first)
   bool store_dirty = true;
 
   // pair state (max_pairs + 1: the last entry is the rst_evaluate scratch pair)
@@ -303,6 +307,35 @@ int32_t rst_ctx_create(int32_t device, int32_t max_w, int32_t max_h, int32_t max
   return RST_OK;
 }
 
+/* (w, h, frames) uint16 tensor over a depth level for the TMA box of k_preprocess (kPreBoxW x kPreBoxH x 1). The
+ * width is the IMAGE width, not the pitch: row padding is out of bounds for the copy engine and reads as zero. */
+static int32_t encode_depth_map(rst_ctx* c, const uint16_t* base, int w, int h, int pitch_px, int64_t frame_px, int frames,
+                                TensorMap* out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+      cudaGetLastError();
+      return fail(c, RST_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    }
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  static_assert(sizeof(TensorMap) == sizeof(CUtensorMap) && alignof(TensorMap) >= alignof(CUtensorMap), "TensorMap must mirror CUtensorMap");
+  const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames};
+  const cuuint64_t strides[2] = {(cuuint64_t)pitch_px * 2, (cuuint64_t)frame_px * 2};   // bytes, dimensions 1 and 2
+  const cuuint32_t box[3] = {(cuuint32_t)kPreBoxW, (cuuint32_t)kPreBoxH, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint16_t*>(base), dims, strides,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(c, RST_ERR_CUDA, ("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")").c_str());
+  return RST_OK;
+}
+
 int32_t rst_begin(rst_ctx* c, int32_t width, int32_t height, const rst_intrinsics* intr,
                   const rst_params* params) {
   if (!c) return RST_ERR_INVALID_ARG;
@@ -370,6 +403,10 @@ int32_t rst_begin(rst_ctx* c, int32_t width, int32_t height, const rst_intrinsic
     c->store_dirty = false;
   }
   c->ext0 = false; c->ext_depth0 = nullptr; c->ext_first = 0; c->ext_count = 0;
+  for (int l = 0; l < P.num_levels; ++l) {
+    const int32_t rc = encode_depth_map(c, c->d_depth[l], c->geom[l].w, c->geom[l].h, c->pitch[l], c->dframe[l], c->max_frames, &c->tmap[l]);
+    if (rc != RST_OK) return rc;
+  }
   c->photo = P.photo_weight > 0.0f;
   if (c->photo && !c->d_rgb) {
     RST_CUDA(c, cudaMalloc(&c->d_rgb, (size_t)c->max_w * c->max_h * 3 * c->max_frames));
@@ -439,6 +476,10 @@ int32_t rst_set_frames_device(rst_ctx* c, const uint16_t* d_depth, int32_t n, in
   if (c->photo) return fail(c, RST_ERR_INVALID_ARG, "the photometric term needs host frames with rgb (rst_upload_frames)");
   if (((uintptr_t)d_depth & 15) || (row_stride_px & 7) || (frame_stride_px & 7))
     return fail(c, RST_ERR_ALIGNMENT, "device depth must be 16-byte aligned with row/frame strides multiples of 8 pixels");
+  {
+    const int32_t rc = encode_depth_map(c, d_depth, c->w, c->h, row_stride_px, frame_stride_px, n, &c->tmap_ext0);
+    if (rc != RST_OK) return rc;
+  }
   c->ext0 = true;
   c->ext_depth0 = d_depth - (int64_t)first_slot * frame_stride_px;
   c->ext_pitch0 = row_stride_px;
@@ -500,8 +541,10 @@ static int32_t preprocess_impl(rst_ctx* c, int first_slot, int n, bool write_geo
     a.first_slot = first_slot;
     a.depth_scale = c->P.depth_scale; a.d_lo = c->d_lo; a.d_span = c->d_span;
     a.normal_depth_tol = c->P.normal_depth_tol; a.pyr_tol = c->P.pyr_depth_tol;
+    const bool ext = l == 0 && c->ext0;
+    a.tmap_slot0 = ext ? c->ext_first : 0;
     const int ph = prof_begin(c, 0, l);
-    RST_CUDA(c, launch_preprocess(a, n, c->stream));
+    RST_CUDA(c, launch_preprocess(a, ext ? c->tmap_ext0 : c->tmap[l], n, c->stream));
     prof_end(c, ph, 1, n);
     c->launches += 1;
   }

@@ -1,8 +1,9 @@
 /*
  * rst_kernels.cuh — argument blocks and launchers of the sm_100a alignment kernels.
  *
- *   K1+K2+K6  k_preprocess : uint16 depth tile (+1 px halo) -> shared memory via 128-bit
- *                            loads; back-projection, normals -> geometry map float4
+ *   K1+K2+K6  k_preprocess : uint16 depth tile (+1 px halo) -> shared memory by ONE TMA tensor
+ *                            copy (cp.async.bulk.tensor.3d, out-of-image pixels zero-filled by
+ *                            the hardware); back-projection, normals -> geometry map float4
  *                            {nx,ny,nz,z}; 2x2 integer pooling -> next pyramid level.
  *   K3+K4+K5  k_icp_fused  : one thread-block cluster per pair, every iteration of every level
  *                            in ONE launch: projective association + point-to-plane
@@ -71,9 +72,17 @@ struct LevelStore {
   int64_t int_frame;
 };
 
+/* a CUtensorMap (128 bytes, 64-byte aligned) without pulling cuda.h into every translation unit */
+struct alignas(64) TensorMap {
+  unsigned long long opaque[16];
+};
+constexpr int kPreBoxW = 80, kPreBoxH = kTileH + 2;   // k_preprocess depth box: 7 pad | 1 halo | 64 | 1 halo | 7 pad columns (the box must
+                                                      // start on a 16-byte boundary of the row: x0 - 8), 1 + 32 + 1 rows
+
 struct PreArgs {
   LevelGeom g;
   LevelStore cur;
+  int32_t tmap_slot0;        // slot of the tensor map's frame 0 (0 for the context's own store)
   uint16_t* next_depth;      // next level (nullable)
   int32_t next_pitch;
   int64_t next_frame;
@@ -155,7 +164,7 @@ struct InitArgs {
   int32_t n_pairs;
 };
 
-cudaError_t launch_preprocess(const PreArgs& a, int n_frames, cudaStream_t s);
+cudaError_t launch_preprocess(const PreArgs& a, const TensorMap& depth_map, int n_frames, cudaStream_t s);
 cudaError_t launch_icp_iter(const IcpArgs& a, int n_pairs, int robust_kind, bool normal_gate,
                             bool write_idx, bool photo, cudaStream_t s);
 cudaError_t launch_icp_fused(const FusedArgs& a, int n_pairs, int cluster, int robust_kind, bool normal_gate,
