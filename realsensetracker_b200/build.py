@@ -68,9 +68,10 @@ def build_align(force: bool = False) -> Path:
 
         def compile_one(src: Path) -> str:
             obj = objdir / (src.stem + ".o")
-            if force or _stale(obj, [src, *hdrs]):
-                return _run([_nvcc(), *NVCC_FLAGS, "-ccbin", HOST_CXX, "-c", "-o", str(obj), str(src)])
-            return ""
+            log = objdir / (src.stem + ".log")   # ptxas -v output of this translation unit (kept across incremental builds)
+            if force or _stale(obj, [src, *hdrs]) or not log.exists():
+                log.write_text(_run([_nvcc(), *NVCC_FLAGS, "-ccbin", HOST_CXX, "-c", "-o", str(obj), str(src)]))
+            return log.read_text()
 
         with ThreadPoolExecutor(max_workers=len(cu)) as ex:
             logs = list(ex.map(compile_one, cu))

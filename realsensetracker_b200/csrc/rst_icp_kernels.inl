@@ -276,14 +276,16 @@ struct PixelPipe {
       if (ROBUST != RST_ROBUST_NONE) {
         // A = sum (sqrt(w) J)(sqrt(w) J)^T: scale the normal (hence J and r) by sqrt(w) once
         float wgt;
+        // IEEE division and square root by their branch-free normal-range sequences: the operands are bounded
+        // (|r| <= dist_max, scale > 0), the weight lies in (0, 1]
         if (ROBUST == RST_ROBUST_HUBER) {
           const float ar = fabsf(r);
-          wgt = ar <= P.robust_scale ? 1.0f : __fdiv_rn(P.robust_scale, ar);
+          wgt = ar <= P.robust_scale ? 1.0f : div_rn_normal(P.robust_scale, ar);
         } else {
-          const float t = __fdiv_rn(P.robust_scale, ffma(r, r, P.robust_scale));
+          const float t = div_rn_normal(P.robust_scale, ffma(r, r, P.robust_scale));
           wgt = fmul(t, t);
         }
-        const float sw = __fsqrt_rn(wgt);
+        const float sw = sqrt_rn_normal(wgt);
         nx = fmul(sw, nx); ny = fmul(sw, ny); nz = fmul(sw, nz); r = fmul(sw, r);
       }
       acc.add(ffma(qy, nz, -fmul(qz, ny)), ffma(qz, nx, -fmul(qx, nz)), ffma(qx, ny, -fmul(qy, nx)), nx, ny, nz, r,
