@@ -47,6 +47,18 @@ struct ChunkPos {
   int v, u;  // row, first column of this lane in the chunk (its two pixels are columns u and u + 32)
 };
 
+// shared-memory landing zone of one pipeline stage: [pixel of the stage][thread], filled by cp.async in K3, read in K4.
+// Photometric variant: also the four bilinear taps of the destination intensity and the source intensity.
+template <bool PHOTO>
+struct StageBuf {
+  float4 g[kPxPerStage][kIcpThreads];
+};
+template <>
+struct StageBuf<true> {
+  float4 g[kPxPerStage][kIcpThreads];
+  float ph[5][kPxPerStage][kIcpThreads];   // I00, I10, I01, I11, I_src
+};
+
 // per-thread state of one pipeline stage: what K4 needs besides the gathered texel. A lane's two pixels of a
 // chunk (columns u and u + 32) share one packed register pair (.x, .y).
 template <bool NGATE, bool WRITE_IDX>
@@ -55,7 +67,6 @@ struct StageRegs {
   float kxq[kPxPerStage], kyq[kPxPerStage];                        // (u'-cx)/fx, (v'-cy)/fy of the target pixel
   float rnx[NGATE ? kPxPerStage : 1], rny[NGATE ? kPxPerStage : 1], rnz[NGATE ? kPxPerStage : 1];  // R * n_src
   int tgt[WRITE_IDX ? kPxPerStage : 1], src[WRITE_IDX ? kPxPerStage : 1];                            // idx_out bookkeeping
-  int spx[kPxPerStage];                                                                               // source pixel index (photometric)
 };
 
 // Gather offset of one source pixel: the target texel's byte offset when every K3 gate holds, else `guard` (an
@@ -172,7 +183,7 @@ struct PixelPipe {
   }
 
   // ---- K3: transform + project the group at `pos`, start the gathers into stage buffer `sbuf`
-  __device__ __forceinline__ void k3(StageRegs<NGATE, WRITE_IDX>& st, float4 (*sbuf)[kIcpThreads]) {
+  __device__ __forceinline__ void k3(StageRegs<NGATE, WRITE_IDX>& st, StageBuf<PHOTO>& sb) {
     const int W = L.W, H = L.H;
     const float cx = L.cx, cy = L.cy, ifx = L.ifx, ify = L.ify;
     ChunkPos p = pos;
@@ -237,8 +248,20 @@ struct PixelPipe {
           st.tgt[e] = off == L.guard ? -1 : (int)(off >> 4);
           st.src[e] = (p.v < H && p.u + 32 * j < W) ? p.v * W + p.u + 32 * j : -1;
         }
-        if (PHOTO) st.spx[e] = p.v * W + p.u + 32 * j;
-        cp_async_16(&sbuf[e][tid], reinterpret_cast<const char*>(L.Gd) + off);
+        cp_async_16(&sb.g[e][tid], reinterpret_cast<const char*>(L.Gd) + off);
+        if constexpr (PHOTO) {
+          // the five intensity values the photometric row of K4 reads ride in the same commit group: bilinear taps of
+          // the destination at floor(u_f), floor(v_f) clamped to the image, and the source pixel's own intensity
+          const float ufj = j ? uf.y : uf.x, vfj = j ? vf.y : vf.x;
+          const int xi = (int)floorf(ufj), yi = (int)floorf(vfj);
+          const int x0 = min(max(xi, 0), W - 1), x1 = min(max(xi + 1, 0), W - 1);
+          const int y0 = min(max(yi, 0), H - 1), y1 = min(max(yi + 1, 0), H - 1);
+          cp_async_4(&sb.ph[0][e][tid], L.Id + y0 * W + x0);
+          cp_async_4(&sb.ph[1][e][tid], L.Id + y0 * W + x1);
+          cp_async_4(&sb.ph[2][e][tid], L.Id + y1 * W + x0);
+          cp_async_4(&sb.ph[3][e][tid], L.Id + y1 * W + x1);
+          cp_async_4(&sb.ph[4][e][tid], L.Is + min(p.v * W + p.u + 32 * j, W * H - 1));
+        }
       }
       if (k + 1 < kChunksPerWarp) next_chunk(p);
     }
@@ -248,14 +271,13 @@ struct PixelPipe {
   }
 
   // ---- K4: gates, residual, Jacobian, branch-free accumulation of one landed stage
-  __device__ __forceinline__ void k4(const StageRegs<NGATE, WRITE_IDX>& st, const float4 (*sbuf)[kIcpThreads]) {
-    const int W = L.W, H = L.H;
+  __device__ __forceinline__ void k4(const StageRegs<NGATE, WRITE_IDX>& st, const StageBuf<PHOTO>& sb) {
 #pragma unroll
     for (int e = 0; e < kPxPerStage; ++e) {
       const int k = e >> 1;
       const float qx = (e & 1) ? st.qx[k].y : st.qx[k].x, qy = (e & 1) ? st.qy[k].y : st.qy[k].x;
       const float qz = (e & 1) ? st.qz[k].y : st.qz[k].x;
-      const float4 g = sbuf[e][tid];
+      const float4 g = sb.g[e][tid];
       const float gz = g.w;
       const float dx = ffma(-st.kxq[e], gz, qx);   // p' - q, q = (kx(u') gz, ky(v') gz, gz) recomputed from the texel's z
       const float dy = ffma(-st.kyq[e], gz, qy);
@@ -290,20 +312,16 @@ struct PixelPipe {
       }
       acc.add(ffma(qy, nz, -fmul(qz, ny)), ffma(qz, nx, -fmul(qx, nz)), ffma(qx, ny, -fmul(qy, nx)), nx, ny, nz, r,
               ok ? 1.0f : 0.0f);
-      if (PHOTO) {
+      if constexpr (PHOTO) {
         // photometric row (f2): r_I = I_dst(pi(p')) - I_src(u,v) by bilinear sampling clamped at the borders,
-        // J_I = [p' x d ; d], d = (dI/du fx/z, dI/dv fy/z, -(d_x x + d_y y)/z), all scaled by sqrt(lambda)
+        // J_I = [p' x d ; d], d = (dI/du fx/z, dI/dv fy/z, -(d_x x + d_y y)/z), all scaled by sqrt(lambda).
+        // The taps were fetched by K3 at the same floor(u_f), floor(v_f) (same expressions, bit for bit).
         const float fx = L.fx, fy = L.fy;
         const float iz = rcp_rn_normal(fmaxf(qz, kMinProjZ));
         const float uf = ffma(fx, fmul(qx, iz), L.cx), vf = ffma(fy, fmul(qy, iz), L.cy);
-        const float x0f = floorf(ok ? uf : 0.0f), y0f = floorf(ok ? vf : 0.0f);
-        const float axf = fsub(ok ? uf : 0.0f, x0f), ayf = fsub(ok ? vf : 0.0f, y0f);
-        const int xi = (int)x0f, yi = (int)y0f;
-        const int x0 = min(max(xi, 0), W - 1), x1 = min(max(xi + 1, 0), W - 1);
-        const int y0 = min(max(yi, 0), H - 1), y1 = min(max(yi + 1, 0), H - 1);
-        const float I00 = __ldg(L.Id + y0 * W + x0), I10 = __ldg(L.Id + y0 * W + x1);
-        const float I01 = __ldg(L.Id + y1 * W + x0), I11 = __ldg(L.Id + y1 * W + x1);
-        const float Isrc = __ldg(L.Is + min(st.spx[e], W * H - 1));
+        const float axf = ok ? fsub(uf, floorf(uf)) : 0.0f, ayf = ok ? fsub(vf, floorf(vf)) : 0.0f;
+        const float I00 = sb.ph[0][e][tid], I10 = sb.ph[1][e][tid], I01 = sb.ph[2][e][tid], I11 = sb.ph[3][e][tid];
+        const float Isrc = sb.ph[4][e][tid];
         const float dt = fsub(I10, I00), db = fsub(I11, I01);
         const float top = ffma(axf, dt, I00), bot = ffma(axf, db, I01);
         const float gv = fsub(bot, top);
@@ -323,7 +341,7 @@ struct PixelPipe {
   //      switches `sd` / `cl` to the next staged depth tile there); the gather pipeline is NOT drained at a tile
   //      boundary.
   template <int TILE_GROUPS, class TileFn>   // TILE_GROUPS: even, or 0 = one tile holds everything
-  __device__ __forceinline__ void run(int n, float4 (*s_g)[kPxPerStage][kIcpThreads], TileFn&& tile) {
+  __device__ __forceinline__ void run(int n, StageBuf<PHOTO>* s_g, TileFn&& tile) {
     static_assert(TILE_GROUPS % 2 == 0, "tile boundaries must fall on even groups");
     if (n <= 0) return;
     StageRegs<NGATE, WRITE_IDX> st0, st1;
@@ -543,7 +561,9 @@ __global__ void __launch_bounds__(kIcpThreads, PHOTO ? 3 : (ROBUST != RST_ROBUST
 k_icp_iter(const __grid_constant__ IcpArgs a) {
   // gathered destination texels land here through cp.async: [stage][pixel][thread], 16 B each, so the
   // two-deep gather pipeline costs no registers and every LDS.128 is conflict-free
-  __shared__ float4 s_g[2][kPxPerStage][kIcpThreads];
+  // the two stage buffers live in dynamic shared memory: the photometric variants exceed the 48 KB static limit
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  StageBuf<PHOTO>* s_g = reinterpret_cast<StageBuf<PHOTO>*>(s_dyn);
   // source depth of the whole block (<= 8192 px), staged once with 16-byte zero-filling cp.async
   __shared__ __align__(16) uint32_t s_d[kMaxGroups * kChunksPerBlock][32];
   __shared__ float s_warp[kIcpThreads / 32][kAccPad];
@@ -674,7 +694,9 @@ constexpr int kTileChunks = kTileGroups * kChunksPerBlock;   // 64 chunks = 4096
 template <int ROBUST, bool NGATE, bool PHOTO>
 __global__ void __launch_bounds__(kIcpThreads, PHOTO ? 3 : (ROBUST != RST_ROBUST_NONE || NGATE) ? 4 : RST_FUSED_MINB)
 k_icp_fused(const __grid_constant__ FusedArgs a) {
-  __shared__ float4 s_g[2][kPxPerStage][kIcpThreads];
+  // the two stage buffers live in dynamic shared memory: the photometric variants exceed the 48 KB static limit
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  StageBuf<PHOTO>* s_g = reinterpret_cast<StageBuf<PHOTO>*>(s_dyn);
   __shared__ __align__(16) uint32_t s_d[2][kTileChunks][32];   // double-buffered source-depth tiles
   __shared__ float s_warp[kIcpThreads / 32][kAccPad];
   __shared__ float s_part[kAccPad];     // this CTA's 29 sums of the current iteration (the leader reads them through DSMEM)
@@ -802,21 +824,37 @@ k_icp_fused(const __grid_constant__ FusedArgs a) {
 // ----------------------------------------------------------------------------------
 // launchers
 // ----------------------------------------------------------------------------------
+// dynamic shared memory of one block (the stage buffers); beyond 48 KB in total the kernel has to opt in once
+template <bool PHOTO, class Kern>
+static cudaError_t stage_smem_opt_in(Kern kern, bool* done) {
+  if (PHOTO && !*done) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(StageBuf<PHOTO>)));
+    if (e != cudaSuccess) return e;
+    *done = true;
+  }
+  return cudaSuccess;
+}
+
 template <int ROBUST, bool NGATE, bool WRITE_IDX, bool PHOTO, bool EARLY>
 static cudaError_t launch_icp_t(const IcpArgs& a, int n_pairs, cudaStream_t s) {
   dim3 grid(a.blocks_per_pair, n_pairs);
+  auto kern = k_icp_iter<ROBUST, NGATE, WRITE_IDX, PHOTO, EARLY>;
+  static bool opted = false;
+  if (cudaError_t e = stage_smem_opt_in<PHOTO>(kern, &opted)) return e;
+  const size_t smem = 2 * sizeof(StageBuf<PHOTO>);
   if (a.pdl) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(kIcpThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k_icp_iter<ROBUST, NGATE, WRITE_IDX, PHOTO, EARLY>, a);
+    return cudaLaunchKernelEx(&cfg, kern, a);
   }
-  k_icp_iter<ROBUST, NGATE, WRITE_IDX, PHOTO, EARLY><<<grid, kIcpThreads, 0, s>>>(a);
+  kern<<<grid, kIcpThreads, smem, s>>>(a);
   return cudaGetLastError();
 }
 
@@ -839,10 +877,12 @@ static cudaError_t launch_fused_t(const FusedArgs& a, int n_pairs, int cluster, 
       allowed = true;
     }
   }
+  static bool opted = false;
+  if (cudaError_t e = stage_smem_opt_in<PHOTO>(kern, &opted)) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(cluster, n_pairs, 1);
   cfg.blockDim = dim3(kIcpThreads, 1, 1);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = 2 * sizeof(StageBuf<PHOTO>);
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -949,6 +989,7 @@ int fused_max_active_clusters(int cluster) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(cluster, 1024, 1);
   cfg.blockDim = dim3(kIcpThreads, 1, 1);
+  cfg.dynamicSmemBytes = 2 * sizeof(StageBuf<false>);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
