@@ -315,6 +315,13 @@ int32_t rst_evaluate(rst_ctx* ctx, int32_t src_slot, int32_t dst_slot,
  * Translation * Quaternion round trip (:151), fixed max_iter iterations, returns
  * mean_cost = sqrt(cost/N) of the last iteration's pre-update correspondences (:157-160).
  * Clouds are xyz-interleaved fp32 (the memory of Cloud3f = Eigen 3xN column-major), HOST pointers.
+ *
+ * What "exact" covers: for the same input pose the neighbour indices and the weights are bit-identical to the
+ * reference algorithm (transform and squared distance in the reference's operation order, no contraction). Equal
+ * distances resolve to the LOWEST index; nanoflann resolves them in tree-traversal order, so on clouds with exactly
+ * tied neighbours the index may differ (the distance never does). Centroids are accumulated in fp64 (the reference:
+ * sequential fp32) and the pose composition / determinant / eigen-solvers are ordinary device fp32 (FMA contraction
+ * allowed): covariances agree to 1e-4 relative and poses to 1e-4 m / 1e-4 rad, not bit for bit.
  * ---------------------------------------------------------------------- */
 typedef struct rst_cloud {
   const float* xyz;  /* n x 3 */
