@@ -150,3 +150,38 @@ def test_graph_replay_is_bit_identical_to_direct_launches(seq_small):
         assert np.array_equal(T3_g, T3_d) and not np.array_equal(T3_g, T2_g)
     finally:
         al.close()
+
+
+def test_frames_bound_in_place_with_ragged_width_and_dirty_padding():
+    """Level 0 read in place from caller memory whose rows are wider than the image, with plausible depth values in the
+    padding, a width that is not a multiple of 8 and a first slot > 0: the TMA tensor of k_preprocess (image width as
+    its extent) and the bulk-staged depth tile of k_icp_iter (padding masked after the copy) must both treat the
+    padding as invalid — geometry maps, association and poses bit-identical to the upload path."""
+    import torch
+    from realsensetracker_b200 import synth
+    w, h = 204, 150                                    # 204 % 8 == 4
+    intr = (122.0, 122.0, 101.5, 74.5)
+    scene = synth.Scene(5)
+    Twc = synth.trajectory(3, seed=5, step_t=0.02, step_r=0.015)
+    frames = np.stack([scene.render(Twc[k], w, h, intr=intr) for k in range(3)])
+    P = default_params()
+    al = Aligner(w, h, 4, 3)
+    try:
+        T_up, st_up = al.align_sequence(frames, intr, P)
+        geo_up = [al.read_geometry(0, l).copy() for l in range(3)]
+        idx_up, ev_up = al.evaluate(1, 0, 0, np.eye(4))
+        pitch = 224                                    # > roundup(w, 8) = 208
+        buf = torch.full((3, h, pitch), 2500, dtype=torch.int16, device="cuda")   # 2.5 m everywhere, padding included
+        buf[:, :, :w] = torch.from_numpy(frames.view(np.int16)).cuda()
+        al.begin(w, h, intr, P)
+        al.set_frames_device(buf.data_ptr(), 3, pitch, pitch * h, first_slot=1)    # slots 1, 2, 3
+        al.preprocess(1, 3)
+        for l in range(3):
+            assert np.array_equal(al.read_geometry(1, l).view(np.uint32), geo_up[l].view(np.uint32)), f"geometry level {l}"
+        idx_d, ev_d = al.evaluate(2, 1, 0, np.eye(4))
+        assert np.array_equal(idx_d, idx_up) and ev_d.count == ev_up.count
+        T_d, st_d = al.align_slots([2, 3], [1, 2])
+        assert np.array_equal(T_d, T_up)
+        assert [s.count for s in st_d] == [s.count for s in st_up]
+    finally:
+        al.close()
