@@ -1,18 +1,22 @@
 /*
- * rst_icp_kernels.cu — K3 + K4 + K5: projective association, point-to-plane residual / Jacobian, the 29-sum
- * reduction and the on-device 6x6 solve, as two kernels over ONE shared per-lane pixel pipeline (PixelPipe):
+ * rst_icp_kernels.inl — K3 + K4 + K5: projective association, point-to-plane residual / Jacobian, the 29-sum
+ * reduction and the on-device 6x6 solve, as two kernels over ONE shared per-lane pixel pipeline (PixelPipe).
+ * Compiled once per slice of the kernel variants (rst_icp_part*.cu, see the end of this file).
  *
- *   k_icp_fused : the product path. One thread-block CLUSTER owns one frame pair and runs EVERY iteration of
- *                 EVERY pyramid level inside a single launch: each CTA walks its share of the level's pixels
- *                 (source depth streamed through a double-buffered shared-memory tile), the CTAs' 29 partial
- *                 sums are combined in fixed rank order through distributed shared memory by the leader CTA,
- *                 which solves (fp64 Cholesky), updates the fp64 master pose and hands the fp32 pose of the
- *                 next iteration back through DSMEM; two cluster barriers per iteration, no global partials,
- *                 no tickets, no fences, no launch per iteration.
- *   k_icp_iter  : one launch = one iteration of one level over a grid of (blocks per pair) x (pairs), block
- *                 partials in global memory, last block of a pair (ticket) reduces and solves. Kept for the
- *                 single-evaluation entry point (rst_evaluate: association index dump, no pose update) and as
- *                 the per-iteration schedule (rst_set_schedule) against which the fused kernel is measured.
+ *   k_icp_iter  : the default schedule. One launch = one iteration of one level over a grid of
+ *                 (blocks per pair) x (pairs): the block's source depth arrives by bulk async copies (UBLKCP +
+ *                 mbarrier), block partials go to global memory, the last block of a pair (ticket) reduces them in
+ *                 fp64 in a fixed order, solves and updates the pose. Also the single-evaluation entry point
+ *                 (rst_evaluate: association index dump, no pose update). Small batches chain their launches with
+ *                 programmatic dependent launch.
+ *   k_icp_fused : one thread-block CLUSTER owns one frame pair and runs EVERY iteration of the chosen pyramid
+ *                 levels inside a single launch: each CTA walks its share of the level's pixels (source depth
+ *                 streamed through a double-buffered shared-memory tile), the CTAs' 29 partial sums are combined
+ *                 in fixed rank order through distributed shared memory by the leader CTA, which solves (fp64
+ *                 Cholesky), updates the fp64 master pose and hands the fp32 pose of the next iteration back
+ *                 through DSMEM; two cluster barriers per iteration, no global partials, no tickets, no launch
+ *                 per iteration. Selectable (rst_set_schedule: fused / hybrid); measured slower than one launch
+ *                 per iteration at 128 pairs, so it is not the default.
  *
  * Nearest reference counterpart: the correspondence + weight loop, covariance accumulation and closed-form
  * solve of AlignIcp3d, align_icp.cpp:101-151. Arithmetic specification: DESIGN.md §3.

@@ -5,15 +5,16 @@
  *                            copy (cp.async.bulk.tensor.3d, out-of-image pixels zero-filled by
  *                            the hardware); back-projection, normals -> geometry map float4
  *                            {nx,ny,nz,z}; 2x2 integer pooling -> next pyramid level.
- *   K3+K4+K5  k_icp_fused  : one thread-block cluster per pair, every iteration of every level
- *                            in ONE launch: projective association + point-to-plane
- *                            residual/Jacobian, 29 sums per thread -> warp shuffle tree ->
- *                            block tree -> cluster totals through distributed shared memory in
- *                            fixed rank order (fp64) -> 6x6 Cholesky + SE(3) update on the
- *                            leader CTA -> pose of the next iteration back through DSMEM.
- *             k_icp_iter   : the same pixel pipeline, one launch per iteration (block partials
- *                            in global memory, last block of a pair reduces and solves);
- *                            rst_evaluate and the per-iteration schedule.
+ *   K3+K4+K5  k_icp_iter   : one launch per iteration (default): depth tile by bulk async copy,
+ *                            projective association + point-to-plane residual/Jacobian, 29
+ *                            sums per thread -> warp shuffle tree -> block tree -> block
+ *                            partials in global memory -> last block of a pair reduces in
+ *                            fp64, 6x6 Cholesky + SE(3) update; also rst_evaluate.
+ *             k_icp_fused  : the same pixel pipeline, one thread-block cluster per pair, every
+ *                            iteration of the chosen levels in ONE launch: cluster totals
+ *                            through distributed shared memory in fixed rank order (fp64),
+ *                            solve on the leader CTA, next pose back through DSMEM
+ *                            (selectable schedule).
  *   k_init_pairs           : pose upload -> fp64 master pose, state reset.
  *
  * Nearest reference counterparts: align_icp.cpp:101-151 (correspondence loop,
