@@ -703,10 +703,13 @@ static int32_t pairs_iterate(rst_ctx* c, int first, int n) {
     if (a.done) RST_CUDA(c, cudaMemsetAsync(c->d_done + first, 0, (size_t)n, c->stream));  // every level starts active
     const int ph = prof_begin(c, 1, l);
     int nl = 0;
-    // small batches (the latency path): consecutive iteration launches overlap head and tail (programmatic dependent
-    // launch); large batches keep plain stream order — there the early blocks of the next launch would only take
-    // SM slots from the running one
+    // consecutive iteration launches are chained with programmatic dependent launch: the next launch's blocks run their
+    // pose-independent head (parameter setup, depth staging) while this launch reduces and solves. Small batches (the
+    // latency path) let the next launch come up at once (pdl 1); large batches only when a block has left its pixel loop
+    // (pdl 2: earlier, the waiting blocks would take SM slots from blocks that still have pixels to process; +2.2 %
+    // at 128 pairs). RST_PDL_LARGE=0 restores plain stream order for large batches.
     a.pdl = (c->pdl_max_pairs > 0 && n <= c->pdl_max_pairs && !c->profiling) ? 1 : 0;
+    if (!a.pdl && !c->profiling) { static const int big = [] { const char* e = std::getenv("RST_PDL_LARGE"); return e ? std::atoi(e) : 2; }(); a.pdl = big; }
     for (int it = 0; it < c->P.iters[l]; ++it) {
       for (int off = 0; off < n; off += 65535) {
         a.pair_offset = first + off;

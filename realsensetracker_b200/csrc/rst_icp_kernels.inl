@@ -601,7 +601,7 @@ k_icp_iter(const __grid_constant__ IcpArgs a) {
   // Programmatic dependent launch (small batches, the latency path): the next iteration's launch may start while this
   // one is still in its reduction / solve tail, and runs its pose-independent head (parameter setup, depth staging)
   // under it; everything the previous launch writes (pose, done flag, tickets) is read after griddepcontrol.wait.
-  if (a.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (a.pdl == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (!a.pdl) pipe.set_pose(a.pose_f32 + 12 * pair);
   pipe.acc.clear();
   {  // first chunk of this warp in group 0; later chunks/groups are reached by adding strides
@@ -641,6 +641,10 @@ k_icp_iter(const __grid_constant__ IcpArgs a) {
   }
   pipe.sd = s_d; pipe.cl = warp * kChunksPerWarp;
   pipe.template run<0>(a.groups, s_g, [](int) {});
+  // pdl == 2 (large batches): the next launch may start only now, when this block has left its pixel loop — its
+  // blocks then come up while the last blocks of this launch reduce and solve, instead of competing for SM slots
+  // with blocks that still have pixels to process
+  if (a.pdl == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   // ---- K5 stage 1
   const float bs = block_reduce29(pipe.acc, s_warp, tid, lane, warp);
