@@ -477,12 +477,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
 // Measured on B200, 14 k-point clouds, 128 iterations: one pair 13.4 ms (C = 1) -> 4.6 ms (C = 16) including the
 // depth -> cloud stage; 8 pairs 14.1 -> 5.9 ms (C = 8; C = 16: 7.8 ms).
 cudaError_t launch_icp3d(const PairDesc* descs, int n_pairs, int max_iter, float grid_cell, int forced, cudaStream_t stream) {
-  static int sm_count = 0, c_max = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    c_max = 8;
+  static int sm_counts[64] = {0}, c_maxs[64] = {0};   // per device ordinal (function attributes are per device)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int di = dev < 64 ? dev : 63;
+  if (sm_counts[di] == 0 || dev >= 64) {
+    cudaDeviceGetAttribute(&sm_counts[di], cudaDevAttrMultiProcessorCount, dev);
+    c_maxs[di] = 8;
     if (cudaFuncSetAttribute(k_icp3d<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(16, 1, 1);
@@ -492,10 +493,11 @@ cudaError_t launch_icp3d(const PairDesc* descs, int n_pairs, int max_iter, float
       at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, k_icp3d<true>, &cfg) == cudaSuccess && n >= 1) c_max = 16;
+      if (cudaOccupancyMaxActiveClusters(&n, k_icp3d<true>, &cfg) == cudaSuccess && n >= 1) c_maxs[di] = 16;
     }
     cudaGetLastError();
   }
+  const int sm_count = sm_counts[di], c_max = c_maxs[di];
   if (forced <= 0)
     if (const char* e = std::getenv("RST_ICP3D_CLUSTER")) forced = std::atoi(e);
   int C = 1;

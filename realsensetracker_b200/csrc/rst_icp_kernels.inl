@@ -832,13 +832,24 @@ k_icp_fused(const __grid_constant__ FusedArgs a) {
 // ----------------------------------------------------------------------------------
 // launchers
 // ----------------------------------------------------------------------------------
+// Function attributes are per device: `done` is a bit mask over device ordinals (a process may hold contexts on
+// several GPUs; ordinals >= 64 simply set the attribute on every launch).
+static bool attr_done(uint64_t* done, int* dev_out) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  *dev_out = dev;
+  return dev < 64 && ((*done >> dev) & 1ull);
+}
+static void attr_mark(uint64_t* done, int dev) { if (dev < 64) *done |= 1ull << dev; }
+
 // dynamic shared memory of one block (the stage buffers); beyond 48 KB in total the kernel has to opt in once
 template <bool PHOTO, class Kern>
-static cudaError_t stage_smem_opt_in(Kern kern, bool* done) {
-  if (PHOTO && !*done) {
+static cudaError_t stage_smem_opt_in(Kern kern, uint64_t* done) {
+  int dev;
+  if (PHOTO && !attr_done(done, &dev)) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(StageBuf<PHOTO>)));
     if (e != cudaSuccess) return e;
-    *done = true;
+    attr_mark(done, dev);
   }
   return cudaSuccess;
 }
@@ -847,7 +858,7 @@ template <int ROBUST, bool NGATE, bool WRITE_IDX, bool PHOTO, bool EARLY>
 static cudaError_t launch_icp_t(const IcpArgs& a, int n_pairs, cudaStream_t s) {
   dim3 grid(a.blocks_per_pair, n_pairs);
   auto kern = k_icp_iter<ROBUST, NGATE, WRITE_IDX, PHOTO, EARLY>;
-  static bool opted = false;
+  static uint64_t opted = 0;
   if (cudaError_t e = stage_smem_opt_in<PHOTO>(kern, &opted)) return e;
   const size_t smem = 2 * sizeof(StageBuf<PHOTO>);
   if (a.pdl) {
@@ -877,15 +888,16 @@ cudaError_t launch_icp_r(const IcpArgs& a, int n_pairs, bool ngate, bool widx, c
 template <int ROBUST, bool NGATE, bool PHOTO>
 static cudaError_t launch_fused_t(const FusedArgs& a, int n_pairs, int cluster, cudaStream_t s) {
   auto kern = k_icp_fused<ROBUST, NGATE, PHOTO>;
-  if (cluster > 8) {   // beyond the portable cluster size: opt in once per instantiation
-    static bool allowed = false;
-    if (!allowed) {
+  if (cluster > 8) {   // beyond the portable cluster size: opt in once per instantiation and device
+    static uint64_t allowed = 0;
+    int dev;
+    if (!attr_done(&allowed, &dev)) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
       if (e != cudaSuccess) return e;
-      allowed = true;
+      attr_mark(&allowed, dev);
     }
   }
-  static bool opted = false;
+  static uint64_t opted = 0;
   if (cudaError_t e = stage_smem_opt_in<PHOTO>(kern, &opted)) return e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(cluster, n_pairs, 1);

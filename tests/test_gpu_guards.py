@@ -185,3 +185,36 @@ def test_frames_bound_in_place_with_ragged_width_and_dirty_padding():
         assert [s.count for s in st_d] == [s.count for s in st_up]
     finally:
         al.close()
+
+
+def test_two_devices_in_one_process(seq_small):
+    """One process, one context per GPU: kernel attributes (dynamic shared memory of the photometric variant, opt-in
+    cluster sizes) are per device, and both devices must give the same bits."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    frames, gt, intr = seq_small
+    n, h, w = frames.shape
+    rgb = np.ascontiguousarray(np.repeat((frames >> 4).astype(np.uint8)[..., None], 3, axis=-1))
+    src, dst = O_clouds()
+    out = []
+    for dev in (0, 1):
+        al = Aligner(w, h, 2 * n, n, device=dev)
+        try:
+            P = default_params()
+            T, _ = al.align_sequence(frames, intr, P)
+            Pp = default_params(photo_weight=0.5)
+            Tp, _ = al.align_pairs(frames[1:], frames[:-1], intr, Pp, src_rgb=rgb[1:], dst_rgb=rgb[:-1])
+            al.set_icp3d_cluster(16)
+            ok, Tc = al.icp3d_pairs([src], [dst], 16)
+            out.append((T, Tp, Tc))
+        finally:
+            al.close()
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+
+
+def O_clouds():
+    from conftest import ROOT
+    g = np.load(ROOT / "tests" / "golden" / "oracle_r.npz")
+    return g["src"], g["dst"]
