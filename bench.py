@@ -543,6 +543,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                 "ours_not_worse_on_every_pair": bool(np.all(errs[:n_cpu, 0] <= cerr[:, 0] + 1e-4) and np.all(errs[:n_cpu, 1] <= cerr[:, 1] + 1e-4)),
                 "note": "different algorithms by the north star's definition: the pose difference is the reference's own error, not ours "
                         "(tests/test_vs_reference.py asserts ours <= reference against ground truth, with the reference compiled from its own source)"}
+            rate1, _, _, _ = cpu_reference_rate(frames, intr, 3, 1)    # as the reference itself runs: one thread
             from oracle import oracle as O
             t0n = time.perf_counter()
             O.align_pair(frames[1], frames[0], intr, O.default_params())
@@ -552,6 +553,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                              f"own align_icp.cpp compiled against stand-in headers) "
                              f"on the first {n_cpu} pairs of the same sequence, one pair per thread, {dt:.1f} s wall",
                    "pose_err_vs_gt": {"t_m_max": float(cerr[:, 0].max()), "r_rad_max": float(cerr[:, 1].max())},
+                   "reference_path_1thread_pairs_per_s": rate1,
                    "same_algorithm_port_1thread_pairs_per_s": 1.0 / dtn}
         # the reference's OWN algorithm on the GPU (rst_icp3d_depth: back-project -> voxel 0.05 -> AlignIcp3d 128 it),
         # host frames in, poses out — the same-algorithm comparison for the CPU figure above

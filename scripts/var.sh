@@ -1,6 +1,6 @@
 #!/bin/bash
 # runs a short bench for each kernel variant in _lib/variants (experiments only); prints value, level-0 launch, pre-processing ms
-for v in default realsensetracker_b200/_lib/variants/*.so; do
+for v in default $(ls realsensetracker_b200/_lib/variants/*.so 2>/dev/null); do
   if [ "$v" = default ]; then unset RST_ALIGN_LIB; else export RST_ALIGN_LIB=$v; fi
   python bench.py --steps 30 --warmup 5 --no-cpu --quick 2>/dev/null | python -c "
 import json,sys,re; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
