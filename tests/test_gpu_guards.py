@@ -218,3 +218,44 @@ def O_clouds():
     from conftest import ROOT
     g = np.load(ROOT / "tests" / "golden" / "oracle_r.npz")
     return g["src"], g["dst"]
+
+
+@pytest.mark.parametrize("size", [(72, 40), (33, 17), (130, 66)])
+def test_small_and_odd_frames_match_the_oracle(size):
+    """Frames smaller than one pre-processing tile / TMA box (80 x 34) and odd sizes: pyramid, geometry maps and
+    association bit-exact against Oracle-N on every level, poses within 1e-4."""
+    from oracle import oracle as O
+    from realsensetracker_b200 import synth
+    w, h = size
+    levels = 3 if min(w, h) >= 32 else 2
+    intr = (0.6 * w, 0.6 * w, 0.5 * w - 0.5, 0.5 * h - 0.5)
+    scene = synth.Scene(7)
+    Twc = synth.trajectory(2, seed=7, step_t=0.01, step_r=0.01)
+    frames = np.stack([scene.render(Twc[k], w, h, intr=intr) for k in range(2)])
+    iters = [4, 3, 2, 0][:levels] + [0] * (4 - levels)
+    P, Po = default_params(num_levels=levels, iters=iters, min_count=6), O.default_params(num_levels=levels, iters=iters, min_count=6)
+    al = Aligner(w, h, 2, 1)
+    try:
+        al.begin(w, h, intr, P)
+        al.upload(frames)
+        al.preprocess(0, 2)
+        d = frames[0]
+        for l in range(levels):
+            L = O.level_info(intr, w, h, l)
+            if l > 0:
+                d = O.pyr_down(d, Po.pyr_depth_tol)
+            assert np.array_equal(al.read_depth(0, l), d)
+            assert np.array_equal(al.read_geometry(0, l).view(np.uint32), O.geometry(d, L, Po).view(np.uint32)), f"level {l}"
+        L0 = O.level_info(intr, w, h, 0)
+        idx_o, st_o = O.evaluate(frames[1], None, O.geometry(frames[0], L0, Po), L0, Po, np.eye(4))
+        idx_g, st_g = al.evaluate(1, 0, 0, np.eye(4))
+        assert np.array_equal(idx_g, idx_o) and st_g.count == st_o.count
+        T, st = al.align_sequence(frames, intr, P)
+        To, so = O.align_pair(frames[1], frames[0], intr, Po)
+        if so.status == 0:
+            dt, dr = synth.pose_error(T[0], To)
+            assert st[0].status == 0 and dt < 1e-4 and dr < 1e-4, (dt, dr)
+        else:
+            assert st[0].status != 0
+    finally:
+        al.close()
