@@ -667,7 +667,14 @@ k_icp_iter(const __grid_constant__ IcpArgs a) {
     double s = 0.0;
     if (col < kAcc) {
       const float* __restrict__ base = a.partials + (int64_t)pair * a.max_blocks * kAccPad + col;
-      for (int b = sub; b < a.blocks_per_pair; b += 8) s += (double)__ldcg(base + (int64_t)b * kAccPad);
+      // four loads in flight, added in index order (the summation order is part of the specification)
+      for (int b0 = sub; b0 < a.blocks_per_pair; b0 += 32) {
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const int b = b0 + 8 * q; v[q] = b < a.blocks_per_pair ? __ldcg(base + (int64_t)b * kAccPad) : 0.0f; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (b0 + 8 * q < a.blocks_per_pair) s += (double)v[q];
+      }
     }
     s += __shfl_xor_sync(0xffffffffu, s, 4);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
