@@ -599,8 +599,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                     "api": "rst_align_sequence_async + rst_wait, two contexts per GPU alternating (copy of step k+1 under the kernels of step k)",
                     "h2d_ceiling": h2d_ceiling},
             "blocking_call": {"value": blocking_value, "unit": "pairs/s", "ms_per_step": ms_blk / max(5, args.steps // 2),
-                              "api": "rst_align_sequence: ONE context, one blocking call per step (H2D, then kernels, then D2H; nothing overlapped) — "
-                                     "what a caller written like the reference's loop gets"},
+                              "api": "rst_align_sequence: ONE context, one blocking call per step — what a caller written like the reference's loop "
+                                     "gets (the call runs the batch as two halves, the upload of the second under the kernels of the first)"},
             "sustained": sustained,
             "latency": latency,
             "configs": configs_extra,

@@ -206,9 +206,10 @@ int32_t rst_align_sequence_async(rst_ctx* ctx, const rst_frame* frames, int32_t 
                                  const float* poses_in);
 int32_t rst_wait(rst_ctx* ctx, float* poses_out, rst_stats* stats_out);
 
-/* The two host-frame calls above upload and process their frames in chunks so that the
- * H2D copy of chunk k+1 (on an internal copy stream) overlaps the kernels of chunk k.
- * `frames_per_chunk` <= 0 disables the chunking (one upload, then one pass; the default).
+/* The host-frame calls can upload and process their frames in chunks so that the H2D copy of chunk k+1 (on an
+ * internal copy stream) overlaps the kernels of chunk k. `frames_per_chunk` > 0: that many frames (pairs) per chunk;
+ * 0 (default): automatic — blocking calls on at least 64 frames / 32 pairs run as two halves, asynchronous calls are
+ * not chunked (their caller overlaps whole calls on two contexts); < 0: never.
  * The chunk size never changes results: every pair is reduced in image-size-determined blocks. */
 int32_t rst_set_pipeline_chunk(rst_ctx* ctx, int32_t frames_per_chunk);
 

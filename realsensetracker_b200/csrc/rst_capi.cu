@@ -85,7 +85,7 @@ struct rst_ctx {
   int cluster_size[2] = {4, 8};         // CTAs per pair of the fused kernel, by rst_params.tiling (throughput, latency)
   int split_ways = 2;                   // measured on B200: 2, 3 and 4 ways are equal (2.18 ms per 128-pair step)
   int split_min_pairs = 32;             // batches of at least this many pairs iterate as two halves on two streams
-  int pipeline_chunk = 0;               // frames (pairs) per upload/compute chunk of the host entry points
+  int pipeline_chunk = 0;               // frames (pairs) per upload/compute chunk of the host entry points; 0 = automatic, < 0 = never
   void* ext = nullptr;                  // state of the cloud-based engine (rst_icp3d.cu), created on first use
   void (*ext_free)(void*) = nullptr;
   // CUDA graphs of the kernel part of small blocking calls (the latency path): a replay costs one enqueue instead
@@ -886,7 +886,7 @@ int32_t rst_max_active_clusters(rst_ctx* c, int32_t ctas_per_pair) {
 
 int32_t rst_set_pipeline_chunk(rst_ctx* c, int32_t frames_per_chunk) {
   if (!c) return RST_ERR_INVALID_ARG;
-  c->pipeline_chunk = frames_per_chunk > 0 ? frames_per_chunk : 0;
+  c->pipeline_chunk = frames_per_chunk;
   return RST_OK;
 }
 
@@ -970,7 +970,12 @@ static int32_t align_pairs_impl(rst_ctx* c, const rst_frame* src, const rst_fram
   // dst frames in slots [0, n), src frames in [n, 2n)
   std::vector<int32_t> s(n_pairs), d(n_pairs);
   for (int i = 0; i < n_pairs; ++i) { d[i] = i; s[i] = n_pairs + i; }
-  const int chunk = c->pipeline_chunk > 0 && c->pipeline_chunk < n_pairs ? c->pipeline_chunk : n_pairs;
+  // automatic: a BLOCKING call on a large batch runs as two halves, the upload of the second under the kernels of the
+  // first (36.5 k -> 40.6 k pairs/s at 128 pairs of 640x480); an asynchronous call is not chunked — its caller overlaps
+  // whole calls on two contexts, and half batches only cost partial waves there
+  int chunk_cfg = c->pipeline_chunk;
+  if (chunk_cfg == 0) chunk_cfg = (wait && n_pairs >= 32 && !c->profiling) ? (n_pairs + 1) / 2 : -1;
+  const int chunk = chunk_cfg > 0 && chunk_cfg < n_pairs ? chunk_cfg : n_pairs;
   const bool piped = chunk < n_pairs;
   const bool try_graph = !piped && n_pairs <= c->graph_max_pairs && !c->profiling;
   if ((rc = pairs_begin(c, s.data(), d.data(), n_pairs, poses_inout, !try_graph)) != RST_OK) return rc;
@@ -1038,7 +1043,9 @@ static int32_t align_sequence_impl(rst_ctx* c, const rst_frame* frames, int32_t 
   const int n_pairs = n_frames - 1;
   std::vector<int32_t> s(n_pairs), d(n_pairs);
   for (int i = 0; i < n_pairs; ++i) { s[i] = i + 1; d[i] = i; }  // AlignIcp3d(curr, prev): rs_replay_app.cpp:251
-  const int chunk = c->pipeline_chunk > 0 && c->pipeline_chunk < n_frames ? c->pipeline_chunk : n_frames;
+  int chunk_cfg = c->pipeline_chunk;   // see align_pairs_impl
+  if (chunk_cfg == 0) chunk_cfg = (wait && n_frames >= 64 && !c->profiling) ? (n_frames + 1) / 2 : -1;
+  const int chunk = chunk_cfg > 0 && chunk_cfg < n_frames ? chunk_cfg : n_frames;
   const bool piped = chunk < n_frames;
   const bool try_graph = !piped && n_pairs <= c->graph_max_pairs && !c->profiling;
   if ((rc = pairs_begin(c, s.data(), d.data(), n_pairs, poses_inout, !try_graph)) != RST_OK) return rc;

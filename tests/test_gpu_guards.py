@@ -259,3 +259,30 @@ def test_small_and_odd_frames_match_the_oracle(size):
             assert st[0].status != 0
     finally:
         al.close()
+
+
+def test_blocking_call_on_a_large_batch_pipelines_its_upload_without_changing_bits():
+    """A blocking host-frame call on >= 64 frames / 32 pairs runs as two halves (upload of the second under the kernels of
+    the first, rst_set_pipeline_chunk automatic): same bits as the unchunked call and as the asynchronous form."""
+    from realsensetracker_b200 import synth
+    w, h, n = 208, 152, 70
+    intr = synth.intrinsics_for(w, h)
+    frames, gt = synth.render_sequence(n, w, h, seed=4, step_t=0.01, step_r=0.008)
+    P = default_params()
+    al = Aligner(w, h, 2 * n, n)
+    try:
+        al.set_pipeline_chunk(-1)
+        T_plain, st_plain = al.align_sequence(frames, intr, P)
+        Tp_plain, _ = al.align_pairs(frames[1:], frames[:-1], intr, P)
+        al.set_pipeline_chunk(0)                          # automatic (the default)
+        l0 = al.launch_count
+        T_auto, st_auto = al.align_sequence(frames, intr, P)
+        assert al.launch_count - l0 > 30                  # two halves: more launches than the 23 of one pass
+        Tp_auto, _ = al.align_pairs(frames[1:], frames[:-1], intr, P)
+        assert np.array_equal(T_auto, T_plain) and np.array_equal(Tp_auto, Tp_plain) and np.array_equal(Tp_plain, T_plain)
+        assert [s.count for s in st_auto] == [s.count for s in st_plain]
+        al.submit_sequence(frames, intr, P)
+        T_async, _ = al.wait()
+        assert np.array_equal(T_async, T_plain)
+    finally:
+        al.close()
