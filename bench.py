@@ -117,13 +117,26 @@ def bind_to_gpu_numa(props, local_rank: int = 0, local_world: int = 1) -> str:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock / power / throttle reasons sampled while the timed region runs: NVML polled every 5 ms from a thread
+    (the 50-step headline region lasts 0.1 s), `nvidia-smi -lms 50` when pynvml is not importable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, uuid: str | None):
-        self.rows, self.proc, self.t = [], None, None
+    def __init__(self, uuid: str | None, index: int = 0):
+        self.rows, self.proc, self.t, self.nvml, self.stop_flag = [], None, None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid) if uuid else pynvml.nvmlDeviceGetHandleByIndex(index)
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.nvml, self.h = pynvml, h
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"]
         if uuid:
             cmd += ["-i", uuid]
@@ -134,35 +147,52 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = [(getattr(n, "nvmlClocksEventReasonHwSlowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8)), "hw_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)), "hw_thermal_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)), "sw_thermal_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonSwPowerCap", getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)), "sw_power_cap")]
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        mx = float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM))
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                r = int(get_reasons(self.h))
+                self.rows.append((time.time(), (sm, mx, pw, [nm for b, nm in bits if r & b])))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0: float, t1: float) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.06)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sel = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.05] or [r for (_, r) in self.rows]
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in sel:
-            f = [x.strip() for x in r.split(",")]
+            f = [x.strip() for x in line.strip().split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                row = (float(f[0]), float(f[1]), float(f[2]), [nm for nm, val in zip(self.NAMES, f[3:7]) if val.lower().startswith("active")])
             except ValueError:
                 continue
-            for nm, val in zip(names, f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
+            self.rows.append((time.time(), row))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sel = [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (t, r) in self.rows if t0 <= t <= t1 + 0.05] or [r for (_, r) in self.rows]
+        sm = [r[0] for r in sel]; mx = [r[1] for r in sel]; pw = [r[2] for r in sel]
+        reasons = sorted({nm for r in sel for nm in r[3]})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons,
+                "source": "nvml, 5 ms" if self.nvml is not None else "nvidia-smi -lms 50"}
 
 
 # --------------------------------------------------------------------------------------------
