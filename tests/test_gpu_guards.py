@@ -284,5 +284,13 @@ def test_blocking_call_on_a_large_batch_pipelines_its_upload_without_changing_bi
         al.submit_sequence(frames, intr, P)
         T_async, _ = al.wait()
         assert np.array_equal(T_async, T_plain)
+        # the same with colour frames and the photometric term (RGB is uploaded chunk by chunk too)
+        rgb = np.ascontiguousarray(np.repeat((frames >> 4).astype(np.uint8)[..., None], 3, axis=-1))
+        Pp = default_params(photo_weight=0.5)
+        al.set_pipeline_chunk(-1)
+        Tc_plain, _ = al.align_pairs(frames[1:41], frames[0:40], intr, Pp, src_rgb=rgb[1:41], dst_rgb=rgb[0:40])
+        al.set_pipeline_chunk(0)
+        Tc_auto, _ = al.align_pairs(frames[1:41], frames[0:40], intr, Pp, src_rgb=rgb[1:41], dst_rgb=rgb[0:40])
+        assert np.array_equal(Tc_auto, Tc_plain) and not np.array_equal(Tc_plain, Tp_plain[:40])
     finally:
         al.close()
