@@ -561,7 +561,7 @@ __device__ __forceinline__ void write_pose_outputs(const double* Rt, float* f12,
 // k_icp_iter: one iteration of one level. grid (blocks_per_pair, n_pairs), kIcpThreads threads.
 // ----------------------------------------------------------------------------------
 template <int ROBUST, bool NGATE, bool WRITE_IDX, bool PHOTO, bool EARLY>
-__global__ void __launch_bounds__(kIcpThreads, PHOTO ? 3 : (ROBUST != RST_ROBUST_NONE || NGATE || WRITE_IDX) ? 4 : RST_ICP_MINB)
+__global__ void __launch_bounds__(kIcpThreads, (PHOTO || ROBUST != RST_ROBUST_NONE || NGATE || WRITE_IDX) ? 4 : RST_ICP_MINB)
 k_icp_iter(const __grid_constant__ IcpArgs a) {
   // gathered destination texels land here through cp.async: [stage][pixel][thread], 16 B each, so the
   // two-deep gather pipeline costs no registers and every LDS.128 is conflict-free
