@@ -662,24 +662,34 @@ k_icp_iter(const __grid_constant__ IcpArgs a) {
   if (!s_last) return;
   __threadfence();
 
-  for (int col = tid >> 3; col < kAccPad; col += kIcpThreads >> 3) {  // warp-uniform trip count
-    const int sub = tid & 7;
-    double s = 0.0;
-    if (col < kAcc) {
-      const float* __restrict__ base = a.partials + (int64_t)pair * a.max_blocks * kAccPad + col;
-      // four loads in flight, added in index order (the summation order is part of the specification)
-      for (int b0 = sub; b0 < a.blocks_per_pair; b0 += 32) {
-        float v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { const int b = b0 + 8 * q; v[q] = b < a.blocks_per_pair ? __ldcg(base + (int64_t)b * kAccPad) : 0.0f; }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) if (b0 + 8 * q < a.blocks_per_pair) s += (double)v[q];
-      }
+  // Column c of the block partials is summed by 8 lanes (lane `sub` takes blocks sub, sub + 8, ... in index order),
+  // then a 4/2/1 tree over the lanes: that order is part of the specification. The first 64 threads each own four
+  // adjacent columns and fetch them as ONE float4 per block, five blocks in flight: the 150 partial rows of a pair in
+  // the latency tiling cost 4 L2 round trips instead of 10 x 2.
+  if (tid < 64) {   // two whole warps: the shuffles below are warp-uniform
+    const int sub = tid & 7, cg4 = (tid >> 3) * 4;
+    const float4* __restrict__ base = reinterpret_cast<const float4*>(a.partials + (int64_t)pair * a.max_blocks * kAccPad + cg4);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int b0 = sub; b0 < a.blocks_per_pair; b0 += 40) {
+      const int b1 = b0 + 8, b2 = b0 + 16, b3 = b0 + 24, b4 = b0 + 32, nb = a.blocks_per_pair;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 v0 = __ldcg(base + (int64_t)b0 * (kAccPad / 4));
+      const float4 v1 = b1 < nb ? __ldcg(base + (int64_t)b1 * (kAccPad / 4)) : z;
+      const float4 v2 = b2 < nb ? __ldcg(base + (int64_t)b2 * (kAccPad / 4)) : z;
+      const float4 v3 = b3 < nb ? __ldcg(base + (int64_t)b3 * (kAccPad / 4)) : z;
+      const float4 v4 = b4 < nb ? __ldcg(base + (int64_t)b4 * (kAccPad / 4)) : z;
+      s0 += (double)v0.x; s1 += (double)v0.y; s2 += (double)v0.z; s3 += (double)v0.w;
+      if (b1 < nb) { s0 += (double)v1.x; s1 += (double)v1.y; s2 += (double)v1.z; s3 += (double)v1.w; }
+      if (b2 < nb) { s0 += (double)v2.x; s1 += (double)v2.y; s2 += (double)v2.z; s3 += (double)v2.w; }
+      if (b3 < nb) { s0 += (double)v3.x; s1 += (double)v3.y; s2 += (double)v3.z; s3 += (double)v3.w; }
+      if (b4 < nb) { s0 += (double)v4.x; s1 += (double)v4.y; s2 += (double)v4.z; s3 += (double)v4.w; }
     }
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    if (sub == 0 && col < kAcc) s_tot[col] = s;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+    }
+    if (sub == 0) { s_tot[cg4] = s0; s_tot[cg4 + 1] = s1; s_tot[cg4 + 2] = s2; s_tot[cg4 + 3] = s3; }   // columns >= kAcc: zeros, unused
   }
   __syncthreads();
   if (tid == 0) {
