@@ -352,6 +352,19 @@ int32_t rst_icp3d_pairs(rst_ctx* ctx, const rst_cloud* src, const rst_cloud* dst
  * pose). */
 int32_t rst_set_icp3d_cluster(rst_ctx* ctx, int32_t ctas_per_pair);
 
+/* Neighbour cache of the cloud ICP kernel. The reference queries its k-d tree for every source point in every one of the
+ * 128 iterations (align_icp.cpp:105-113). Here a query that has to search scans `margin` further than the candidate
+ * neighbour requires and records how far every OTHER target point is proven to be; in later iterations the triangle
+ * inequality |p' - nbr| + |p' - p| < L shows, for most points, that the neighbour cannot have changed, and the search is
+ * skipped. The neighbour index and its fp32 squared distance are the ones a search would return, bit for bit — only
+ * the time changes. margin = clamp(gain * motion of the point since its last search, lo_cells * cell, hi_cells * cell).
+ * hi_cells = 0 switches the cache off (every point searches in every iteration). Defaults: 4, 0.05, 0.5. */
+int32_t rst_set_icp3d_cache(rst_ctx* ctx, float gain, float lo_cells, float hi_cells);
+
+/* Of the last rst_icp3d_pairs / rst_icp3d_depth call of this context: how many neighbour queries were answered
+ * (source points x iterations, over all pairs) and how many of them had to search (the rest were proven by the cache). */
+int32_t rst_icp3d_cache_stats(rst_ctx* ctx, uint64_t* searched_out, uint64_t* queried_out);
+
 /* bool SolveKabsch(src, dst, indices, weights, &xfm)  (align_icp.hpp:14-18, align_icp.cpp:18-71) on the device:
  * closed-form pose from GIVEN (src index, dst index) pairs — the initialiser rs_align_app.cpp:295 feeds to
  * AlignIcp3d. `pairs`: n_pairs x 2 int32; `weights`: n_pairs floats or NULL (the reference's empty vector);

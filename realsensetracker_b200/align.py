@@ -340,6 +340,16 @@ class Aligner:
         """CTAs per pair of the cloud ICP kernel: 0 = automatic, or 1 / 2 / 4 / 8 / 16."""
         self._check(self._lib.rst_set_icp3d_cluster(self._ctx, ctas_per_pair))
 
+    def set_icp3d_cache(self, gain: float = 4.0, lo_cells: float = 0.05, hi_cells: float = 0.5):
+        """Neighbour cache of the cloud ICP kernel (scan margin = clamp(gain * motion, lo, hi) in grid cells); hi_cells = 0: off."""
+        self._check(self._lib.rst_set_icp3d_cache(self._ctx, gain, lo_cells, hi_cells))
+
+    def icp3d_cache_stats(self):
+        """(neighbour queries that searched, neighbour queries answered) of the last cloud-ICP call."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._lib.rst_icp3d_cache_stats(self._ctx, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def set_schedule(self, schedule: int):
         """0 = fused (one cluster per pair, all iterations in one launch; default), 1 = one launch per iteration."""
         self._check(self._lib.rst_set_schedule(self._ctx, schedule))

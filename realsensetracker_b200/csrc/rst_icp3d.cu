@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include <cfloat>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -27,11 +28,21 @@
 #include "rst_device.cuh"
 #include "rst_internal.h"
 
+// -DRST_ICP3D_PROFILE: block 0 prints the cycles thread 0 spent in every phase of the iteration loop (experiments only)
+#ifdef RST_ICP3D_PROFILE
+#define PHASE(k) do { const long long now_ = clock64(); ph_[k] += now_ - t_; t_ = now_; } while (0)
+#else
+#define PHASE(k) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
 constexpr int kCellCap = 1 << 18;  // grid cells per pair (1 MiB of cell_start)
+constexpr int kRingBytes = 8 * kThreads * 16;   // dynamic shared memory of k_icp3d (OwnStream)
+constexpr int kGroupScanMax = 2048;   // queued points per CTA up to which a search is spread over kScanLanes lanes
+constexpr float kCacheGain = 4.0f, kCacheLo = 0.05f, kCacheHi = 0.5f;   // neighbour-cache scan margin (see nn_ball)
 
 struct PairDesc {
   const float* src;   // n x 3
@@ -44,6 +55,10 @@ struct PairDesc {
   float4* sorted;     // m: x, y, z, original index (bit pattern)
   int* nbr;           // n
   float* w;           // n
+  float4* sl;         // n   (source point, neighbour cache: proven radius L | iteration tag)
+  float4* qd;         // n   (coordinates of the current neighbour, squared distance to it)
+  int* queue;         // n + 16 * kThreads: source points whose neighbour has to be searched this iteration
+  unsigned long long* stat;   // [2]: neighbour searches done, neighbour queries answered (zeroed by the host)
   float* pose;        // 16, column-major, in/out
   rst_icp3d_result* res;
 };
@@ -57,6 +72,17 @@ __device__ __forceinline__ float mulrn(float a, float b) { return __fmul_rn(a, b
 __device__ __forceinline__ float addrn(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float subrn(float a, float b) { return __fsub_rn(a, b); }
 
+// hi + lo += x without rounding error (Knuth's TwoSum; adds only, so nothing for the compiler to contract). A thread's
+// partial sum kept this way carries ~48 significant bits — the fp64 accumulation of fp32 terms the reference
+// specifies (align_icp.cpp:124-136) to within 1e-14 — without a float -> double conversion and a DADD per term
+// (those two made the covariance pass the longest phase of an iteration: 13 issue cycles per term on B200).
+__device__ __forceinline__ void acc2(float& hi, float& lo, float x) {
+  const float s = __fadd_rn(hi, x);
+  const float bb = __fsub_rn(s, hi);
+  lo = __fadd_rn(lo, __fadd_rn(__fsub_rn(hi, __fsub_rn(s, bb)), __fsub_rn(x, bb)));
+  hi = s;
+}
+
 // block-wide sum of K doubles, fixed order (xor tree inside a warp, warps in index order)
 template <int K>
 __device__ void block_sum(double (&v)[K], double (*s_part)[16], double* s_out) {
@@ -69,10 +95,11 @@ __device__ void block_sum(double (&v)[K], double (*s_part)[16], double* s_out) {
     if (lane == 0) s_part[warp][k] = x;
   }
   __syncthreads();
-  if (threadIdx.x < K) {
-    double x = 0.0;
-    for (int w = 0; w < kWarps; ++w) x += s_part[w][threadIdx.x];
-    s_out[threadIdx.x] = x;
+  if (warp < K) {   // warp k adds the 32 warp sums of component k (xor tree again)
+    double x = s_part[lane][warp];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) s_out[warp] = x;
   }
   __syncthreads();
 }
@@ -216,15 +243,23 @@ __device__ void nn_search(const Grid& g, const int* __restrict__ cell_start, con
 // the true nearest neighbour — and every point tying with it — lies inside the ball of radius
 // |p - candidate| around p, so only the cells that ball overlaps are scanned (typically 1-8 instead
 // of the 27+ of a ring search). Same result as nn_search: smallest fp32 d2, ties to the lowest index.
-__device__ void nn_refine(const Grid& g, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
-                          const float* __restrict__ dst, float px, float py, float pz, int cand, int* best_j, float* best_d2) {
-  float bd;
+//
+// The ball is scanned `margin` wider than needed, and the scan also tracks the second-smallest distance it
+// meets: afterwards every dst point other than the winner is PROVEN to lie at least L = min(second distance,
+// scanned radius) away from p. The caller keeps (p, L) with the neighbour (the neighbour cache): while a later query
+// p' of the same source point satisfies |p' - nbr| + |p' - p| < L, the triangle inequality makes nbr the strict
+// nearest neighbour of p' as well, and the search is skipped — same index, same fp32 d2, bit for bit.
+__device__ void nn_ball(const Grid& g, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
+                        const float* __restrict__ dst, float px, float py, float pz, int cand, float margin, int* best_j,
+                        float* best_d2, float* proven) {
+  float bd, sd = FLT_MAX;   // best and second-best squared distance (second: any index other than the best's)
   int bj = cand;
   {
     const float dx = subrn(px, dst[3 * cand]), dy = subrn(py, dst[3 * cand + 1]), dz = subrn(pz, dst[3 * cand + 2]);
     bd = addrn(addrn(mulrn(dx, dx), mulrn(dy, dy)), mulrn(dz, dz));
   }
-  const float rad = sqrtf(bd) * 1.0001f + 1e-3f * g.h;  // inflated: rounding of d2 and of the cell assignment
+  const float rad_sure = sqrtf(bd) * 1.0001f + margin;   // every point within rad_sure of p is examined
+  const float rad = rad_sure + 1e-3f * g.h;               // inflated: rounding of d2 and of the cell assignment
   const int x0 = cell_coord(px - rad, g.lox, g.inv_h, g.nx), x1 = cell_coord(px + rad, g.lox, g.inv_h, g.nx);
   const int y0 = cell_coord(py - rad, g.loy, g.inv_h, g.ny), y1 = cell_coord(py + rad, g.loy, g.inv_h, g.ny);
   const int z0 = cell_coord(pz - rad, g.loz, g.inv_h, g.nz), z1 = cell_coord(pz + rad, g.loz, g.inv_h, g.nz);
@@ -238,28 +273,85 @@ __device__ void nn_refine(const Grid& g, const int* __restrict__ cell_start, con
         const float dx = subrn(px, q.x), dy = subrn(py, q.y), dz = subrn(pz, q.z);
         const float d2 = addrn(addrn(mulrn(dx, dx), mulrn(dy, dy)), mulrn(dz, dz));
         const int j = __float_as_int(q.w);
-        if (d2 < bd || (d2 == bd && j < bj)) { bd = d2; bj = j; }
+        if (d2 < bd || (d2 == bd && j < bj)) { sd = bd; bd = d2; bj = j; }   // the old best is the new runner-up
+        else if (j != bj) sd = fminf(sd, d2);
       }
     }
   *best_j = bj;
   *best_d2 = bd;
+  *proven = fminf(sqrtf(sd), rad_sure) * 0.9998f;
 }
 
-// R = U V^T of a 3x3 fp64 matrix by one-sided Jacobi (row-major in/out)
-__device__ void svd_uvt(const double* M, double* UVt) {
-  double B[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-  for (int i = 0; i < 9; ++i) B[i] = M[i];
+// nn_ball by kScanLanes consecutive lanes of a warp for ONE query (all of them pass the same arguments; `active` = the group
+// has a query): the (z, y) rows of the ball's box are dealt out over the lanes, every lane keeps the best and second
+// best of its rows, and a butterfly merges them — the latency of a search is one or two rows instead of all of them.
+// Used when few points of a CTA have to search (most iterations): the whole CTA waits for them at a barrier. Every
+// lane of the warp must call it (full-mask shuffles). Same results as nn_ball, bit for bit.
+constexpr int kScanLanes = 8;
+__device__ void nn_ball_group(const Grid& g, const int* __restrict__ cell_start, const float4* __restrict__ sorted,
+                              const float* __restrict__ dst, bool active, float px, float py, float pz, int cand, float margin,
+                              int* best_j, float* best_d2, float* proven) {
+  float bd = FLT_MAX, sd = FLT_MAX, rad_sure = 0.f, dc2 = FLT_MAX;
+  int bj = 0x7fffffff;
+  if (active) {
+    const float cx = subrn(px, dst[3 * cand]), cy = subrn(py, dst[3 * cand + 1]), cz = subrn(pz, dst[3 * cand + 2]);
+    dc2 = addrn(addrn(mulrn(cx, cx), mulrn(cy, cy)), mulrn(cz, cz));
+    rad_sure = sqrtf(dc2) * 1.0001f + margin;
+    const float rad = rad_sure + 1e-3f * g.h;
+    const int x0 = cell_coord(px - rad, g.lox, g.inv_h, g.nx), x1 = cell_coord(px + rad, g.lox, g.inv_h, g.nx);
+    const int y0 = cell_coord(py - rad, g.loy, g.inv_h, g.ny), y1 = cell_coord(py + rad, g.loy, g.inv_h, g.ny);
+    const int z0 = cell_coord(pz - rad, g.loz, g.inv_h, g.nz), z1 = cell_coord(pz + rad, g.loz, g.inv_h, g.nz);
+    const int ny = y1 - y0 + 1, rows = ny * (z1 - z0 + 1);
+    for (int r = threadIdx.x & (kScanLanes - 1); r < rows; r += kScanLanes) {
+      const int row = ((z0 + r / ny) * g.ny + y0 + r % ny) * g.nx;
+      const int e = cell_start[row + x1 + 1];
+      for (int k = cell_start[row + x0]; k < e; ++k) {
+        const float4 q = sorted[k];
+        const float dx = subrn(px, q.x), dy = subrn(py, q.y), dz = subrn(pz, q.z);
+        const float d2 = addrn(addrn(mulrn(dx, dx), mulrn(dy, dy)), mulrn(dz, dz));
+        const int j = __float_as_int(q.w);
+        if (d2 < bd || (d2 == bd && j < bj)) { sd = bd; bd = d2; bj = j; }
+        else sd = fminf(sd, d2);   // a lane meets every point once: j != bj here
+      }
+    }
+  }
+#pragma unroll
+  for (int o = kScanLanes / 2; o > 0; o >>= 1) {   // the lanes' candidates are disjoint: the loser's best is a runner-up
+    const float obd = __shfl_xor_sync(0xffffffffu, bd, o), osd = __shfl_xor_sync(0xffffffffu, sd, o);
+    const int obj = __shfl_xor_sync(0xffffffffu, bj, o);
+    const bool take = obd < bd || (obd == bd && obj < bj);
+    sd = fminf(fminf(sd, osd), take ? bd : obd);
+    if (take) { bd = obd; bj = obj; }
+  }
+  if (bj == 0x7fffffff) { bj = cand; bd = dc2; }   // nothing met (a non-finite candidate): as nn_ball, which starts from it
+  *best_j = bj;
+  *best_d2 = bd;
+  *proven = fminf(sqrtf(sd), rad_sure) * 0.9998f;
+}
+
+// R = U V^T of a 3x3 fp64 matrix by one-sided Jacobi (row-major in/out). V (in/out, orthogonal) is the right basis the
+// sweeps start from and the one they end with: the identity for a cold start, the previous ICP iteration's result for
+// a warm one — consecutive cross-covariances differ little, so B = M V then has nearly orthogonal columns already and
+// one or two sweeps finish the job instead of five. The rotation (c, s) that zeroes the column product gamma comes
+// without a division or a square root: with tau = beta - alpha, kappa = 2 gamma, rho = |(tau, kappa)|,
+//   c = (|tau| + rho) / sqrt(2 rho (rho + |tau|)),  s = sign(tau) kappa / sqrt(2 rho (rho + |tau|))
+// (the same angle as t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = tau / kappa), two reciprocal square roots.
+__device__ void svd_uvt(const double* M, double* UVt, double* V) {
+  double B[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) B[3 * i + j] = M[3 * i] * V[j] + M[3 * i + 1] * V[3 + j] + M[3 * i + 2] * V[6 + j];
   for (int sweep = 0; sweep < 60; ++sweep) {
-    double off = 0.0;
+    bool rotated = false;
     for (int p = 0; p < 2; ++p)
       for (int q = p + 1; q < 3; ++q) {
         double a = 0, b = 0, c = 0;
         for (int i = 0; i < 3; ++i) { a += B[3 * i + p] * B[3 * i + p]; b += B[3 * i + q] * B[3 * i + q]; c += B[3 * i + p] * B[3 * i + q]; }
-        off = fmax(off, fabs(c) / sqrt(a * b + 1e-300));
-        if (fabs(c) <= 1e-300) continue;
-        const double zeta = (b - a) / (2.0 * c);
-        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+        if (!(c * c > 1e-30 * (a * b))) continue;   // |c| <= 1e-15 sqrt(a b): the two columns are orthogonal
+        rotated = true;
+        const double tau = b - a, kappa = 2.0 * c, s2 = tau * tau + kappa * kappa;
+        const double rho = s2 * rsqrt(s2), at = fabs(tau);
+        const double r = rsqrt(2.0 * rho * (rho + at));
+        const double cs = (at + rho) * r, sn = (tau >= 0 ? kappa : -kappa) * r;
         for (int i = 0; i < 3; ++i) {
           const double bp = B[3 * i + p], bq = B[3 * i + q];
           B[3 * i + p] = cs * bp - sn * bq; B[3 * i + q] = sn * bp + cs * bq;
@@ -267,14 +359,18 @@ __device__ void svd_uvt(const double* M, double* UVt) {
           V[3 * i + p] = cs * vp - sn * vq; V[3 * i + q] = sn * vp + cs * vq;
         }
       }
-    if (off < 1e-15) break;
+    if (!rotated) break;
   }
-  double U[9], s[3];
-  for (int j = 0; j < 3; ++j) s[j] = sqrt(B[j] * B[j] + B[3 + j] * B[3 + j] + B[6 + j] * B[6 + j]);
+  double U[9], s[3], inv[3];
+  for (int j = 0; j < 3; ++j) {
+    const double n2 = B[j] * B[j] + B[3 + j] * B[3 + j] + B[6 + j] * B[6 + j];
+    inv[j] = rsqrt(n2);
+    s[j] = n2 > 0 ? n2 * inv[j] : 0.0;
+  }
   const double smax = fmax(s[0], fmax(s[1], s[2]));
   int bad = -1;
   for (int j = 0; j < 3; ++j) {
-    if (s[j] > 1e-14 * smax && s[j] > 0) { for (int i = 0; i < 3; ++i) U[3 * i + j] = B[3 * i + j] / s[j]; }
+    if (s[j] > 1e-14 * smax && s[j] > 0) { for (int i = 0; i < 3; ++i) U[3 * i + j] = B[3 * i + j] * inv[j]; }
     else bad = j;
   }
   if (bad >= 0) {  // rank-deficient covariance: complete the basis with the cross product
@@ -326,6 +422,41 @@ __device__ void compose_pose(const float* R, const float* t, float* T) {
   T[15] = 1.f;
 }
 
+// A thread's own elements (first, first + stride, ...) of NA float4 arrays, streamed through a per-thread ring in shared
+// memory with cp.async: 7 (one array) or 3 (two arrays) trips are in flight per thread at no register cost. The
+// passes of an iteration are plain sweeps over 0.2-0.5 MB per CTA that lives in L2; with the one or two loads per thread
+// a register-bound 1024-thread CTA can keep in flight they ran at a fifth of the L2 bandwidth.
+// ring: 8 x kThreads float4 of dynamic shared memory; slot s of array r of thread t at ring[(s * NA + r) * kThreads + t].
+template <int NA>
+struct OwnStream {
+  static constexpr int S = 8 / NA;
+  float4* ring;
+  const float4* arr[NA];
+  int first, stride, n;
+  __device__ __forceinline__ void fetch(int trip) {
+    const int i = first + trip * stride;
+    if (i < n) {
+#pragma unroll
+      for (int r = 0; r < NA; ++r)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(ring + ((trip % S) * NA + r) * kThreads + threadIdx.x)),
+                     "l"(arr[r] + i) : "memory");
+    }
+    rst::cp_async_commit();
+  }
+  __device__ __forceinline__ void start() {
+#pragma unroll
+    for (int t = 0; t < S - 1; ++t) fetch(t);
+  }
+  // element `trip` of every array; then the slot read one trip ago (its values are long consumed) takes trip + S - 1
+  __device__ __forceinline__ void get(int trip, float4 (&x)[NA]) {
+    rst::cp_async_wait<S - 2>();
+#pragma unroll
+    for (int r = 0; r < NA; ++r) x[r] = ring[((trip % S) * NA + r) * kThreads + threadIdx.x];
+    fetch(trip + S - 1);
+  }
+  __device__ __forceinline__ void finish() { rst::cp_async_wait<0>(); }
+};
+
 // Sum of K doubles over every thread of the CTAs that share a pair. CL = false: one CTA, block_sum. CL = true: the
 // CTAs of a thread-block cluster; every CTA leaves its block sums in its own shared memory (`s_loc`), and after one
 // cluster barrier every CTA adds the C block sums up in rank order through distributed shared memory — the same total,
@@ -338,11 +469,12 @@ __device__ void pair_sum(double (&v)[K], double (*s_part)[16], double* s_loc, do
   cg::cluster_group cluster = cg::this_cluster();
   block_sum<K>(v, s_part, s_loc);
   cluster.sync();
-  if (threadIdx.x < K) {
+  if ((threadIdx.x >> 5) < K) {   // warp k fetches sum k of every rank at once (one remote load per lane), then adds in rank order
+    const unsigned C = cluster.num_blocks(), lane = threadIdx.x & 31, k = threadIdx.x >> 5;
+    const double mine = lane < C ? cluster.map_shared_rank(s_loc, lane)[k] : 0.0;
     double x = 0.0;
-    const unsigned C = cluster.num_blocks();
-    for (unsigned r = 0; r < C; ++r) x += cluster.map_shared_rank(s_loc, r)[threadIdx.x];
-    s_out[threadIdx.x] = x;
+    for (unsigned r = 0; r < C; ++r) x += __shfl_sync(0xffffffffu, mine, r);
+    if (lane == 0) s_out[k] = x;
   }
   __syncthreads();
 }
@@ -350,11 +482,19 @@ __device__ void pair_sum(double (&v)[K], double (*s_part)[16], double* s_loc, do
 // grid (n_pairs) [CL = false] or (C, n_pairs) in clusters of (C, 1, 1) [CL = true: the C CTAs split the source points
 // of one pair — small batches, where one CTA per pair would leave most of the 148 SMs idle].
 template <bool CL>
-__global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restrict__ descs, int max_iter, float grid_cell) {
+__global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restrict__ descs, int max_iter, float grid_cell, float3 cache) {
   __shared__ double s_part[kWarps][16];
+  __shared__ int s_qn;
+  // s_cum[k & 255]: upper bound of the path length ANY source point has travelled from the initial pose to the pose of
+  // iteration k (sum of per-iteration bounds): a point moved at most s_cum[now] - s_cum[k] since iteration k
+  __shared__ float s_cum[256];
+  __shared__ float s_red[kWarps];
+  __shared__ float s_rmax;
   __shared__ double s_sum[16];
   __shared__ double s_loc[2][16];
+  extern __shared__ float4 s_ring[];   // kRingBytes: the passes' cp.async rings (OwnStream)
   __shared__ float s_T[16];
+  __shared__ double s_V[9];   // right singular vectors of the last solve (thread 0)
   __shared__ Grid s_g0;
   namespace cg = cooperative_groups;
 
@@ -394,59 +534,191 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
     const float inv = (float)(1.0 / (double)P.n);
     for (int a = 0; a < 3; ++a) smean[a] = (float)s_sum[a] * inv;
   }
+  // radius of the source cloud about its centroid (for the neighbour cache's motion bound)
+  {
+    float r2 = 0.f;
+    for (int i = tid; i < P.n; i += kThreads) {
+      const float x = P.src[3 * i] - smean[0], y = P.src[3 * i + 1] - smean[1], z = P.src[3 * i + 2] - smean[2];
+      const float d = x * x + y * y + z * z;
+      r2 = d > r2 ? d : r2;   // a non-finite point never raises it (and never consults the cache)
+    }
+    for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+    if ((tid & 31) == 0) s_red[tid >> 5] = r2;
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < kWarps; ++w) r2 = fmaxf(r2, s_red[w]);
+      s_rmax = sqrtf(r2) * 1.0001f;
+      s_cum[0] = 0.f;
+    }
+    __syncthreads();
+  }
+  const float rmax = s_rmax;
   if (tid < 16) s_T[tid] = P.pose[tid];
+  if (tid < 9) s_V[tid] = tid % 4 == 0 ? 1.0 : 0.0;
+  if (tid == 0) s_qn = 0;
+  // per source point, two 16-byte records so that no pass of an iteration gathers or chases an index:
+  //   sl[i] = (source point, L | k): the proven radius of the neighbour cache with, in its 8 lowest mantissa bits,
+  //           the iteration (mod 256) whose pose the point had when L was proven — that position is recomputed
+  //           from the pose history in shared memory instead of being stored;
+  //   qd[i] = (coordinates of the current neighbour, squared distance to it).
+  for (int i = first; i < P.n; i += stride) {
+    P.sl[i] = make_float4(P.src[3 * i], P.src[3 * i + 1], P.src[3 * i + 2], 0.f);   // L = 0: nothing proven yet
+    P.qd[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   __syncthreads();
+  // this CTA's part of the search queue: it owns at most n / C + kThreads source points
+  int* const queue = P.queue + (CL ? rank * (P.n / (int)cg::this_cluster().num_blocks() + kThreads) : 0);
+  const bool cache_on = cache.z > 0.f;
+  const float kInf = __int_as_float(0x7f800000);
 
   float mu = 1.0f;  // align_icp.cpp:91
   double cost = 0.0;
+  unsigned long long n_searched = 0;
+#ifdef RST_ICP3D_PROFILE
+  long long ph_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_ = clock64();
+#endif
   for (int iter = 0; iter < max_iter; ++iter) {
     if (iter > 0 && iter % 8 == 0) mu = __fdiv_rn(mu, 1.4f);  // :96-98
     float T[12];
     T[0] = s_T[0]; T[1] = s_T[1]; T[2] = s_T[2]; T[3] = s_T[4]; T[4] = s_T[5]; T[5] = s_T[6];
     T[6] = s_T[8]; T[7] = s_T[9]; T[8] = s_T[10]; T[9] = s_T[12]; T[10] = s_T[13]; T[11] = s_T[14];
-    // ---- correspondences + weights (:105-121)
-    double a4[4] = {0, 0, 0, 0};  // cost, sum dst_j
-    for (int i = first; i < P.n; i += stride) {
-      const float sx = P.src[3 * i], sy = P.src[3 * i + 1], sz = P.src[3 * i + 2];
-      // Isometry3f * Vector3f, left to right, no contraction
-      const float px = addrn(addrn(addrn(mulrn(T[0], sx), mulrn(T[3], sy)), mulrn(T[6], sz)), T[9]);
-      const float py = addrn(addrn(addrn(mulrn(T[1], sx), mulrn(T[4], sy)), mulrn(T[7], sz)), T[10]);
-      const float pz = addrn(addrn(addrn(mulrn(T[2], sx), mulrn(T[5], sy)), mulrn(T[8], sz)), T[11]);
-      int j; float d2;
+    const float moved_now = s_cum[iter & 255];   // written by the previous iteration's solve, before its closing barrier
+    PHASE(0);
+    // Isometry3f * Vector3f, left to right, no contraction
+    auto xform = [](const float* M, float sx, float sy, float sz, float& px, float& py, float& pz) {
+      px = addrn(addrn(addrn(mulrn(M[0], sx), mulrn(M[3], sy)), mulrn(M[6], sz)), M[9]);
+      py = addrn(addrn(addrn(mulrn(M[1], sx), mulrn(M[4], sy)), mulrn(M[7], sz)), M[10]);
+      pz = addrn(addrn(addrn(mulrn(M[2], sx), mulrn(M[5], sy)), mulrn(M[8], sz)), M[11]);
+    };
+    // ---- correspondences (:105-113) through the neighbour cache, in three passes over this CTA's source points.
+    // A: transform, distance to the cached neighbour, cache test (see nn_ball); points that fail it are queued.
+    auto pass_a = [&](int i, const float4& a, const float4& b) {
+      float px, py, pz;
+      xform(T, a.x, a.y, a.z, px, py, pz);
       // a non-finite source point or pose (the reference's callers run RemoveNans first) has no neighbour:
       // index 0, d2 = +inf, hence weight 0, cost = inf and ok = 0 — without walking the whole grid for it
-      if (!(isfinite(px) && isfinite(py) && isfinite(pz))) { j = 0; d2 = __int_as_float(0x7f800000); }
-      else if (iter == 0) nn_search(g, P.cell_start, P.sorted, px, py, pz, &j, &d2);
-      else nn_refine(g, P.cell_start, P.sorted, P.dst, px, py, pz, P.nbr[i], &j, &d2);
-      const float rt = __fdiv_rn(mu, addrn(d2, mu));
-      P.nbr[i] = j;
-      P.w[i] = mulrn(rt, rt);
-      a4[0] += (double)d2;
-      a4[1] += (double)P.dst[3 * j]; a4[2] += (double)P.dst[3 * j + 1]; a4[3] += (double)P.dst[3 * j + 2];
+      if (!(isfinite(px) && isfinite(py) && isfinite(pz))) {
+        P.nbr[i] = 0;
+        P.qd[i] = make_float4(P.dst[0], P.dst[1], P.dst[2], kInf);
+        return;
+      }
+      const int age = (iter - __float_as_int(a.w)) & 255;
+      if (cache_on && age < 250) {
+        const float dx = subrn(px, b.x), dy = subrn(py, b.y), dz = subrn(pz, b.z);
+        const float d2c = addrn(addrn(mulrn(dx, dx), mulrn(dy, dy)), mulrn(dz, dz));   // as the scan computes it
+        const float m = __int_as_float(__float_as_int(a.w) & ~255) - (moved_now - s_cum[(iter - age) & 255]);   // L - motion since L was proven
+        if (m > 0.f && d2c * 1.0005f < m * m) { P.qd[i].w = d2c; return; }   // |p - nbr| + motion < L: proven, nbr stays
+      }
+      queue[atomicAdd(&s_qn, 1)] = i;
+    };
+    {
+      OwnStream<2> in{s_ring, {P.sl, P.qd}, first, stride, P.n};
+      in.start();
+      for (int trip = 0, i = first; i < P.n; ++trip, i += stride) {
+        float4 x[2];
+        in.get(trip, x);
+        pass_a(i, x[0], x[1]);
+      }
+      in.finish();
     }
+    PHASE(1);
+    __syncthreads();
+    PHASE(2);
+    // B: the queued points, densely over the CTA's threads: ring search without a candidate (first iteration), then
+    // the ball scan that also renews the cache entry. The margin follows the point's motion since its last scan.
+    const int qn = s_qn;
+    n_searched += qn;
+    if (iter > 0 && qn <= kGroupScanMax) {   // few points search: kScanLanes lanes each, so that the barrier below is reached sooner
+      for (int q0 = 0; q0 < qn; q0 += kThreads / kScanLanes) {
+        const int q = q0 + tid / kScanLanes;
+        const bool active = q < qn;
+        const int i = active ? queue[q] : 0;
+        const float4 a = P.sl[i];
+        float px, py, pz;
+        xform(T, a.x, a.y, a.z, px, py, pz);
+        const int cand = P.nbr[i];
+        const float margin = fminf(fmaxf(cache.x * (moved_now - s_cum[__float_as_int(a.w) & 255]), cache.y * g.h), cache.z * g.h);
+        int j;
+        float d2, L;
+        nn_ball_group(g, P.cell_start, P.sorted, P.dst, active, px, py, pz, cand, cache_on ? margin : 0.f, &j, &d2, &L);
+        if (active && (tid & (kScanLanes - 1)) == 0) {
+          P.nbr[i] = j;
+          P.sl[i].w = __int_as_float((__float_as_int(L) & ~255) | (iter & 255));
+          P.qd[i] = make_float4(P.dst[3 * j], P.dst[3 * j + 1], P.dst[3 * j + 2], d2);
+        }
+      }
+    } else
+    for (int q = tid; q < qn; q += kThreads) {
+      const int i = queue[q];
+      const float4 a = P.sl[i];
+      float px, py, pz;
+      xform(T, a.x, a.y, a.z, px, py, pz);
+      int cand, j;
+      float d2, L, margin = cache.y * g.h;
+      if (iter == 0) nn_search(g, P.cell_start, P.sorted, px, py, pz, &cand, &d2);
+      else {
+        cand = P.nbr[i];
+        margin = fminf(fmaxf(cache.x * (moved_now - s_cum[__float_as_int(a.w) & 255]), margin), cache.z * g.h);
+      }
+      nn_ball(g, P.cell_start, P.sorted, P.dst, px, py, pz, cand, cache_on ? margin : 0.f, &j, &d2, &L);
+      P.nbr[i] = j;
+      P.sl[i].w = __int_as_float((__float_as_int(L) & ~255) | (iter & 255));   // L rounded down, tagged with this iteration
+      P.qd[i] = make_float4(P.dst[3 * j], P.dst[3 * j + 1], P.dst[3 * j + 2], d2);
+    }
+    __syncthreads();
+    PHASE(3);
+    if (tid == 0) s_qn = 0;   // every thread has read qn; visible to the next iteration through pair_sum's barriers
+    // C: cost and the neighbour sum in the fixed per-thread order (four points per trip)
+    float h4[4] = {0, 0, 0, 0}, l4[4] = {0, 0, 0, 0};  // cost, sum dst_j (hi, lo)
+    {
+      OwnStream<1> in{s_ring, {P.qd}, first, stride, P.n};
+      in.start();
+      for (int trip = 0, i = first; i < P.n; ++trip, i += stride) {
+        float4 b[1];
+        in.get(trip, b);
+        acc2(h4[0], l4[0], b[0].w); acc2(h4[1], l4[1], b[0].x); acc2(h4[2], l4[2], b[0].y); acc2(h4[3], l4[3], b[0].z);
+      }
+      in.finish();
+    }
+    double a4[4];
+    for (int k = 0; k < 4; ++k) a4[k] = isfinite(h4[k]) ? (double)h4[k] + (double)l4[k] : (double)h4[k];   // inf - inf in lo otherwise
+    PHASE(4);
     pair_sum<4, CL>(a4, s_part, s_loc[0], s_sum);
+    PHASE(5);
     cost = s_sum[0];
     float dmean[3];
     for (int a = 0; a < 3; ++a) dmean[a] = (float)s_sum[1 + a] / (float)P.n;  // :122, unweighted
-    // ---- weighted cross-covariance: fp32 products, fp64 accumulation (:125-136)
-    double cv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = first; i < P.n; i += stride) {
-      const int j = P.nbr[i];
-      const float w = P.w[i];
-      float ds[3], wd[3];
-      for (int a = 0; a < 3; ++a) {
-        wd[a] = mulrn(w, subrn(P.dst[3 * j + a], dmean[a]));
-        ds[a] = subrn(P.src[3 * i + a], smean[a]);
+    // ---- weights (:114-121) and the weighted cross-covariance: fp32 products, fp64 accumulation (:125-136)
+    float hv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, lv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const bool last = iter == max_iter - 1;
+    {
+      OwnStream<2> in{s_ring, {P.sl, P.qd}, first, stride, P.n};
+      in.start();
+      for (int trip = 0, i = first; i < P.n; ++trip, i += stride) {
+        float4 x[2];   // (source point, .), (neighbour, d2)
+        in.get(trip, x);
+        const float rt = __fdiv_rn(mu, addrn(x[1].w, mu));
+        const float w = mulrn(rt, rt);
+        if (last) P.w[i] = w;
+        const float wd[3] = {mulrn(w, subrn(x[1].x, dmean[0])), mulrn(w, subrn(x[1].y, dmean[1])), mulrn(w, subrn(x[1].z, dmean[2]))};
+        const float ds[3] = {subrn(x[0].x, smean[0]), subrn(x[0].y, smean[1]), subrn(x[0].z, smean[2])};
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc2(hv[3 * a + c], lv[3 * a + c], mulrn(wd[a], ds[c]));
       }
-      for (int a = 0; a < 3; ++a)
-        for (int b = 0; b < 3; ++b) cv[3 * a + b] += (double)mulrn(wd[a], ds[b]);
+      in.finish();
     }
+    double cv[9];
+    for (int k = 0; k < 9; ++k) cv[k] = isfinite(hv[k]) ? (double)hv[k] + (double)lv[k] : (double)hv[k];
+    PHASE(6);
     pair_sum<9, CL>(cv, s_part, s_loc[1], s_sum);
+    PHASE(5);
     // ---- closed-form pose (:139-151); in a cluster every CTA solves from the same totals (no broadcast)
     if (tid == 0) {
       double cov[9], uvt[9];
       for (int k = 0; k < 9; ++k) cov[k] = s_sum[k];
-      svd_uvt(cov, uvt);
+      svd_uvt(cov, uvt, s_V);   // warm start from the previous iteration's right singular vectors
       float R[9], t[3];
       for (int k = 0; k < 9; ++k) R[k] = (float)uvt[k];
       const float det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
@@ -454,13 +726,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
       for (int a = 0; a < 3; ++a) t[a] = dmean[a] - (R[3 * a] * smean[0] + R[3 * a + 1] * smean[1] + R[3 * a + 2] * smean[2]);
       float Tn[16];
       compose_pose(R, t, Tn);
+      {  // |T' s - T s| = |(R' - R)(s - c) + T' c - T c| <= |R' - R|_F rmax + |T' c - T c|, c = the source centroid
+        float f2 = 0.f, cm[3];
+        for (int col = 0; col < 3; ++col)
+          for (int r = 0; r < 3; ++r) { const float d = Tn[4 * col + r] - s_T[4 * col + r]; f2 += d * d; }
+        for (int r = 0; r < 3; ++r)
+          cm[r] = (Tn[r] - s_T[r]) * smean[0] + (Tn[4 + r] - s_T[4 + r]) * smean[1] + (Tn[8 + r] - s_T[8 + r]) * smean[2] + (Tn[12 + r] - s_T[12 + r]);
+        const float step = (sqrtf(f2) * rmax + sqrtf(cm[0] * cm[0] + cm[1] * cm[1] + cm[2] * cm[2])) * 1.001f + 1e-7f * rmax;
+        s_cum[(iter + 1) & 255] = moved_now + step + 2e-7f * moved_now;   // rounded up generously: the sum must not fall short
+      }
       for (int k = 0; k < 16; ++k) s_T[k] = Tn[k];
       if (rank == 0 && P.res && iter == max_iter - 1) for (int k = 0; k < 9; ++k) P.res->cov[k] = cov[k];
     }
     __syncthreads();
+    PHASE(7);
   }
+#ifdef RST_ICP3D_PROFILE
+  if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+    printf("k_icp3d phases (cycles of thread 0, %d iterations): head %lld | pass A %lld | wait A %lld | pass B + wait %lld | pass C %lld | sums %lld | cov %lld | solve %lld\n",
+           max_iter, ph_[0], ph_[1], ph_[2], ph_[3], ph_[4], ph_[5], ph_[6], ph_[7]);
+#endif
+  if (tid == 0) atomicAdd(P.stat, n_searched);
   if (CL) cg::this_cluster().sync();   // nobody leaves while its block sums may still be read
   if (rank != 0) return;
+  if (tid == 0) P.stat[1] = (unsigned long long)P.n * (unsigned long long)max_iter;
   if (tid < 16) P.pose[tid] = s_T[tid];  // :156
   if (tid == 0 && P.res) {
     const float mean_cost = sqrtf((float)cost / (float)P.n);  // :157
@@ -476,7 +765,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
 // C * n_pairs <= SM count, at most 16 — beyond 8 is the opt-in cluster size). RST_ICP3D_CLUSTER overrides.
 // Measured on B200, 14 k-point clouds, 128 iterations: one pair 13.4 ms (C = 1) -> 4.6 ms (C = 16) including the
 // depth -> cloud stage; 8 pairs 14.1 -> 5.9 ms (C = 8; C = 16: 7.8 ms).
-cudaError_t launch_icp3d(const PairDesc* descs, int n_pairs, int max_iter, float grid_cell, int forced, cudaStream_t stream) {
+cudaError_t launch_icp3d(const PairDesc* descs, int n_pairs, int max_iter, float grid_cell, int forced, float3 cache, cudaStream_t stream) {
   static int sm_counts[64] = {0}, c_maxs[64] = {0};   // per device ordinal (function attributes are per device)
   int dev = 0;
   cudaGetDevice(&dev);
@@ -484,10 +773,13 @@ cudaError_t launch_icp3d(const PairDesc* descs, int n_pairs, int max_iter, float
   if (sm_counts[di] == 0 || dev >= 64) {
     cudaDeviceGetAttribute(&sm_counts[di], cudaDevAttrMultiProcessorCount, dev);
     c_maxs[di] = 8;
+    cudaFuncSetAttribute(k_icp3d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes);
+    cudaFuncSetAttribute(k_icp3d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingBytes);
     if (cudaFuncSetAttribute(k_icp3d<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(16, 1, 1);
       cfg.blockDim = dim3(kThreads, 1, 1);
+      cfg.dynamicSmemBytes = kRingBytes;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = 16; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -504,18 +796,19 @@ cudaError_t launch_icp3d(const PairDesc* descs, int n_pairs, int max_iter, float
   if (forced > 0) while (C * 2 <= c_max && C * 2 <= forced) C *= 2;
   else while (C * 2 <= c_max && C * 2 * n_pairs <= (C * 2 > 8 ? sm_count / 2 : sm_count)) C *= 2;   // 16-CTA clusters pack badly: only while they leave half the GPU free
   if (C == 1) {
-    k_icp3d<false><<<n_pairs, kThreads, 0, stream>>>(descs, max_iter, grid_cell);
+    k_icp3d<false><<<n_pairs, kThreads, kRingBytes, stream>>>(descs, max_iter, grid_cell, cache);
     return cudaGetLastError();
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(C, n_pairs, 1);
   cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = kRingBytes;
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_icp3d<true>, descs, max_iter, grid_cell);
+  return cudaLaunchKernelEx(&cfg, k_icp3d<true>, descs, max_iter, grid_cell, cache);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -687,7 +980,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_kabsch(const float* __restrict_
   if (tid == 0) {
     double cov[9], uvt[9];
     for (int k = 0; k < 9; ++k) cov[k] = s_sum[k];
-    svd_uvt(cov, uvt);
+    double V0[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    svd_uvt(cov, uvt, V0);
     float R[9], t[3];
     for (int k = 0; k < 9; ++k) R[k] = (float)uvt[k];
     const float det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
@@ -1116,7 +1410,15 @@ struct Icp3dState {
   int last_frames = 0;
   size_t last_npx = 0, last_cloud_off = 0;
   int icp3d_cluster = 0;   // CTAs per pair of k_icp3d, 0 = automatic
+  // neighbour cache of k_icp3d: scan margin = clamp(x * motion since the last scan, y * cell, z * cell); z <= 0 = off
+  float3 cache = make_float3(kCacheGain, kCacheLo, kCacheHi);
+  unsigned long long searched = 0, queried = 0;   // of the last rst_icp3d_pairs / rst_icp3d_depth call
 };
+
+inline void sum_stats(Icp3dState* st, const unsigned long long* s, int n_pairs) {
+  st->searched = st->queried = 0;
+  for (int i = 0; i < n_pairs; ++i) { st->searched += s[2 * i]; st->queried += s[2 * i + 1]; }
+}
 
 void icp3d_free(void* p) {
   Icp3dState* s = static_cast<Icp3dState*>(p);
@@ -1139,6 +1441,29 @@ extern "C" int32_t rst_set_icp3d_cluster(rst_ctx* c, int32_t ctas_per_pair) {
   void** slot = rst::ctx_ext_slot(c, &free_fn);
   if (!*slot) { *slot = new Icp3dState(); *free_fn = icp3d_free; }
   static_cast<Icp3dState*>(*slot)->icp3d_cluster = ctas_per_pair;
+  return RST_OK;
+}
+
+extern "C" int32_t rst_set_icp3d_cache(rst_ctx* c, float gain, float lo_cells, float hi_cells) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  if (!(gain >= 0.f) || !(lo_cells >= 0.f) || !(hi_cells >= 0.f) || !(hi_cells <= 16.f) || lo_cells > hi_cells) {
+    rst::ctx_set_error(c, "rst_set_icp3d_cache: gain >= 0 and 0 <= lo_cells <= hi_cells <= 16 expected");
+    return RST_ERR_INVALID_ARG;
+  }
+  void (**free_fn)(void*) = nullptr;
+  void** slot = rst::ctx_ext_slot(c, &free_fn);
+  if (!*slot) { *slot = new Icp3dState(); *free_fn = icp3d_free; }
+  static_cast<Icp3dState*>(*slot)->cache = make_float3(gain, lo_cells, hi_cells);
+  return RST_OK;
+}
+
+extern "C" int32_t rst_icp3d_cache_stats(rst_ctx* c, uint64_t* searched_out, uint64_t* queried_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  void (**free_fn)(void*) = nullptr;
+  void** slot = rst::ctx_ext_slot(c, &free_fn);
+  const Icp3dState* st = static_cast<const Icp3dState*>(*slot);
+  if (searched_out) *searched_out = st ? st->searched : 0;
+  if (queried_out) *queried_out = st ? st->queried : 0;
   return RST_OK;
 }
 
@@ -1177,6 +1502,7 @@ extern "C" int32_t rst_icp3d_pairs(rst_ctx* c, const rst_cloud* src, const rst_c
   }
   const size_t upload_bytes = off;
   const size_t o_res = off; off = align_up(off + sizeof(rst_icp3d_result) * n_pairs);
+  const size_t o_stat = off; off = align_up(off + sizeof(unsigned long long) * 2 * n_pairs);
   std::vector<size_t> o_nbr(n_pairs), o_w(n_pairs);
   const size_t o_nbr0 = off;
   for (int i = 0; i < n_pairs; ++i) { o_nbr[i] = off; off += sizeof(int) * (size_t)src[i].n; }
@@ -1185,11 +1511,14 @@ extern "C" int32_t rst_icp3d_pairs(rst_ctx* c, const rst_cloud* src, const rst_c
   for (int i = 0; i < n_pairs; ++i) { o_w[i] = off; off += sizeof(float) * (size_t)src[i].n; }
   off = align_up(off);
   const size_t download_end = off;
-  std::vector<size_t> o_cs(n_pairs), o_cf(n_pairs), o_sorted(n_pairs);
+  std::vector<size_t> o_cs(n_pairs), o_cf(n_pairs), o_sorted(n_pairs), o_sl(n_pairs), o_qd(n_pairs), o_queue(n_pairs);
   for (int i = 0; i < n_pairs; ++i) {
     o_cs[i] = off; off = align_up(off + sizeof(int) * (kCellCap + 1));
     o_cf[i] = off; off = align_up(off + sizeof(int) * kCellCap);
     o_sorted[i] = off; off = align_up(off + sizeof(float4) * (size_t)dst[i].n);
+    o_sl[i] = off; off = align_up(off + sizeof(float4) * (size_t)src[i].n);
+    o_qd[i] = off; off = align_up(off + sizeof(float4) * (size_t)src[i].n);
+    o_queue[i] = off; off = align_up(off + sizeof(int) * ((size_t)src[i].n + 16 * kThreads));
   }
   const size_t total = off;
   if (st->d_bytes < total) {
@@ -1216,14 +1545,17 @@ extern "C" int32_t rst_icp3d_pairs(rst_ctx* c, const rst_cloud* src, const rst_c
     d.cell_start = reinterpret_cast<int*>(D + o_cs[i]); d.cell_fill = reinterpret_cast<int*>(D + o_cf[i]);
     d.sorted = reinterpret_cast<float4*>(D + o_sorted[i]);
     d.nbr = reinterpret_cast<int*>(D + o_nbr[i]); d.w = reinterpret_cast<float*>(D + o_w[i]);
+    d.sl = reinterpret_cast<float4*>(D + o_sl[i]); d.qd = reinterpret_cast<float4*>(D + o_qd[i]);
+    d.queue = reinterpret_cast<int*>(D + o_queue[i]);
     d.pose = reinterpret_cast<float*>(D + o_pose) + 16 * i;
     d.res = reinterpret_cast<rst_icp3d_result*>(D + o_res) + i;
+    d.stat = reinterpret_cast<unsigned long long*>(D + o_stat) + 2 * i;
     hd[i] = d;
   }
   std::memcpy(H + o_pose, poses_inout, sizeof(float) * 16 * n_pairs);
   ICP_CUDA(cudaMemcpyAsync(D, H, upload_bytes, cudaMemcpyHostToDevice, stream));
-  ICP_CUDA(cudaMemsetAsync(D + o_res, 0, sizeof(rst_icp3d_result) * n_pairs, stream));
-  ICP_CUDA(launch_icp3d(reinterpret_cast<const PairDesc*>(D + o_desc), n_pairs, max_iter, grid_cell, st->icp3d_cluster, stream));
+  ICP_CUDA(cudaMemsetAsync(D + o_res, 0, o_nbr0 - o_res, stream));   // results and cache statistics
+  ICP_CUDA(launch_icp3d(reinterpret_cast<const PairDesc*>(D + o_desc), n_pairs, max_iter, grid_cell, st->icp3d_cluster, st->cache, stream));
   rst::ctx_count_launches(c, 1);
   ICP_CUDA(cudaMemcpyAsync(H + o_pose, D + o_pose, sizeof(float) * 16 * n_pairs, cudaMemcpyDeviceToHost, stream));
   const bool want_corr = nbrs_out || weights_out;
@@ -1231,6 +1563,7 @@ extern "C" int32_t rst_icp3d_pairs(rst_ctx* c, const rst_cloud* src, const rst_c
   ICP_CUDA(cudaStreamSynchronize(stream));
   std::memcpy(poses_inout, H + o_pose, sizeof(float) * 16 * n_pairs);
   if (results) std::memcpy(results, H + o_res, sizeof(rst_icp3d_result) * n_pairs);
+  sum_stats(st, reinterpret_cast<const unsigned long long*>(H + o_stat), n_pairs);
   if (nbrs_out) std::memcpy(nbrs_out, H + o_nbr0, sizeof(int) * n_src_total);
   if (weights_out) std::memcpy(weights_out, H + o_w0, sizeof(float) * n_src_total);
 #undef ICP_CUDA
@@ -1280,6 +1613,7 @@ extern "C" int32_t rst_icp3d_depth(rst_ctx* c, const rst_frame* frames, int32_t 
   const size_t upload_bytes = off;
   const size_t o_res = off; off = align_up(off + sizeof(rst_icp3d_result) * (size_t)(n_pairs > 0 ? n_pairs : 1));
   const size_t o_cnt = off; off = align_up(off + sizeof(int) * n_frames);
+  const size_t o_stat = off; off = align_up(off + sizeof(unsigned long long) * 2 * (size_t)(n_pairs > 0 ? n_pairs : 1));
   const size_t download_end = off;
   const size_t o_depth = off; off = align_up(off + npx * 2 * n_frames);
   const size_t o_cloud = off; off = align_up(off + npx * 12 * n_frames);
@@ -1287,13 +1621,17 @@ extern "C" int32_t rst_icp3d_depth(rst_ctx* c, const rst_frame* frames, int32_t 
   const size_t o_vals = off; off = align_up(off + (decimate ? (size_t)cap * 4 * n_frames : 0));
   const int n_seg = (int)((npx + kSegPx - 1) / kSegPx);
   const size_t o_seg = off; off = align_up(off + sizeof(int) * (size_t)n_seg * n_frames);
-  std::vector<size_t> o_cs(n_pairs), o_cf(n_pairs), o_sorted(n_pairs), o_nbr(n_pairs), o_w(n_pairs);
+  std::vector<size_t> o_cs(n_pairs), o_cf(n_pairs), o_sorted(n_pairs), o_nbr(n_pairs), o_w(n_pairs), o_sl(n_pairs), o_qd(n_pairs),
+      o_queue(n_pairs);
   for (int i = 0; i < n_pairs; ++i) {
     o_cs[i] = off; off = align_up(off + sizeof(int) * (kCellCap + 1));
     o_cf[i] = off; off = align_up(off + sizeof(int) * kCellCap);
     o_sorted[i] = off; off = align_up(off + sizeof(float4) * npx);
     o_nbr[i] = off; off = align_up(off + sizeof(int) * npx);
     o_w[i] = off; off = align_up(off + sizeof(float) * npx);
+    o_sl[i] = off; off = align_up(off + sizeof(float4) * npx);
+    o_qd[i] = off; off = align_up(off + sizeof(float4) * npx);
+    o_queue[i] = off; off = align_up(off + sizeof(int) * (npx + 16 * kThreads));
   }
   const size_t total = off;
   if (st->d_bytes < total) {
@@ -1328,8 +1666,11 @@ extern "C" int32_t rst_icp3d_depth(rst_ctx* c, const rst_frame* frames, int32_t 
     d.cell_start = reinterpret_cast<int*>(D + o_cs[i]); d.cell_fill = reinterpret_cast<int*>(D + o_cf[i]);
     d.sorted = reinterpret_cast<float4*>(D + o_sorted[i]);
     d.nbr = reinterpret_cast<int*>(D + o_nbr[i]); d.w = reinterpret_cast<float*>(D + o_w[i]);
+    d.sl = reinterpret_cast<float4*>(D + o_sl[i]); d.qd = reinterpret_cast<float4*>(D + o_qd[i]);
+    d.queue = reinterpret_cast<int*>(D + o_queue[i]);
     d.pose = reinterpret_cast<float*>(D + o_pose) + 16 * i;
     d.res = reinterpret_cast<rst_icp3d_result*>(D + o_res) + i;
+    d.stat = reinterpret_cast<unsigned long long*>(D + o_stat) + 2 * i;
     pd[i] = d;
   }
   if (n_pairs > 0) std::memcpy(H + o_pose, poses_inout, sizeof(float) * 16 * n_pairs);
@@ -1342,6 +1683,7 @@ extern "C" int32_t rst_icp3d_depth(rst_ctx* c, const rst_frame* frames, int32_t 
     ICP_CUDA(cudaMemsetAsync(D + o_vals, 0x7f, (size_t)cap * 4 * n_frames, stream));  // 0x7f7f7f7f > any pixel index
   }
   ICP_CUDA(cudaMemsetAsync(D + o_res, 0, sizeof(rst_icp3d_result) * (size_t)(n_pairs > 0 ? n_pairs : 1), stream));
+  ICP_CUDA(cudaMemsetAsync(D + o_stat, 0, sizeof(unsigned long long) * 2 * (size_t)(n_pairs > 0 ? n_pairs : 1), stream));
   {
     const CloudifyDesc* dd = reinterpret_cast<const CloudifyDesc*>(D + o_cdesc);
     const dim3 gpx((unsigned)((npx + 255) / 256), n_frames), gseg(n_seg, n_frames);
@@ -1353,7 +1695,7 @@ extern "C" int32_t rst_icp3d_depth(rst_ctx* c, const rst_frame* frames, int32_t 
     rst::ctx_count_launches(c, decimate ? 4 : 3);
   }
   if (n_pairs > 0) {
-    ICP_CUDA(launch_icp3d(reinterpret_cast<const PairDesc*>(D + o_pdesc), n_pairs, max_iter, grid_cell, st->icp3d_cluster, stream));
+    ICP_CUDA(launch_icp3d(reinterpret_cast<const PairDesc*>(D + o_pdesc), n_pairs, max_iter, grid_cell, st->icp3d_cluster, st->cache, stream));
     rst::ctx_count_launches(c, 1);
     ICP_CUDA(cudaMemcpyAsync(H + o_pose, D + o_pose, sizeof(float) * 16 * n_pairs, cudaMemcpyDeviceToHost, stream));
   }
@@ -1362,6 +1704,7 @@ extern "C" int32_t rst_icp3d_depth(rst_ctx* c, const rst_frame* frames, int32_t 
   if (n_pairs > 0) std::memcpy(poses_inout, H + o_pose, sizeof(float) * 16 * n_pairs);
   if (results && n_pairs > 0) std::memcpy(results, H + o_res, sizeof(rst_icp3d_result) * n_pairs);
   if (counts_out) std::memcpy(counts_out, H + o_cnt, sizeof(int) * n_frames);
+  sum_stats(st, reinterpret_cast<const unsigned long long*>(H + o_stat), n_pairs);
 #undef ICP_CUDA
   return RST_OK;
 }

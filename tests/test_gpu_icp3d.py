@@ -193,3 +193,30 @@ def test_cluster_per_pair_agrees_with_one_cta_per_pair(al):
         assert not ok_d[0] and np.array_equal(T_d[0], np.eye(4, dtype=np.float32))
     finally:
         al.set_icp3d_cluster(0)
+
+
+def test_neighbour_cache_changes_nothing_but_time(al):
+    """rst_set_icp3d_cache: the cached neighbour is kept only when the triangle inequality proves a search would return
+    it, so 128 iterations with the cache (any margin setting, any cluster size) give the same neighbours, weights,
+    covariance and pose as 128 iterations that search every point every time — bit for bit."""
+    src, dst = depth_clouds(1, 0)
+    src2, dst2 = GOLD["src"], GOLD["dst"]
+    T0 = synth.make_pose(synth.rotvec_to_R([0.01, -0.02, 0.01]), [0.02, 0.01, -0.03])
+    try:
+        for cl in (1, 4):
+            al.set_icp3d_cluster(cl)
+            al.set_icp3d_cache(0.0, 0.0, 0.0)
+            ok0, Ta, ex0 = al.icp3d_pairs([src, src2], [dst, dst2], 128, T0=T0, details=True)
+            for setting in ((4.0, 0.05, 0.5), (0.0, 0.0, 0.01), (8.0, 0.5, 2.0)):
+                al.set_icp3d_cache(*setting)
+                for cell in (0.1, 0.0):
+                    ok1, Tb, ex1 = al.icp3d_pairs([src, src2], [dst, dst2], 128, T0=T0, grid_cell=cell, details=True)
+                    assert np.array_equal(Ta, Tb), (cl, setting, cell)
+                    for i in range(2):
+                        assert np.array_equal(ex0[i]["nbrs"], ex1[i]["nbrs"]) and np.array_equal(ex0[i]["weights"], ex1[i]["weights"])
+                        assert np.array_equal(ex0[i]["cov"], ex1[i]["cov"]) and ex0[i]["mean_cost"] == ex1[i]["mean_cost"]
+        with pytest.raises(Exception):
+            al.set_icp3d_cache(1.0, 2.0, 1.0)       # lo > hi
+    finally:
+        al.set_icp3d_cluster(0)
+        al.set_icp3d_cache()
