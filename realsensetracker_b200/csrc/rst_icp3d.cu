@@ -83,25 +83,49 @@ __device__ __forceinline__ void acc2(float& hi, float& lo, float x) {
   hi = s;
 }
 
-// block-wide sum of K doubles, fixed order (xor tree inside a warp, warps in index order)
-template <int K>
+// block-wide sum of K doubles, fixed order. Inside a warp a transposed butterfly: at every step a lane passes one half
+// of the components it still holds to its partner and adds the partner's other half to its own, so that K (padded to a
+// power of two) components over 32 lanes cost about K shuffles instead of 5 K — shuffles were what a 1024-thread CTA
+// spent most of a reduction on. Then warp k adds the 32 warp sums of component k (xor tree).
+template <int K, bool PUSH = false>
 __device__ void block_sum(double (&v)[K], double (*s_part)[16], double* s_out) {
+  constexpr int KP = K <= 1 ? 1 : K <= 2 ? 2 : K <= 4 ? 4 : K <= 8 ? 8 : 16;
+  static_assert(K <= 16 && kWarps == 32, "block_sum: at most 16 components, 32 warps");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double x[KP];
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    double x = v[k];
+  for (int k = 0; k < KP; ++k) x[k] = k < K ? v[k] : 0.0;
+  int comp = 0;   // the component this lane ends up with
+  int o = 16;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    if (lane == 0) s_part[warp][k] = x;
+  for (int cnt = KP; cnt > 1; cnt >>= 1, o >>= 1) {
+    const bool upper = (lane & o) != 0;
+    comp = 2 * comp + (upper ? 1 : 0);
+#pragma unroll
+    for (int k = 0; k < cnt / 2; ++k) {
+      const double send = upper ? x[k] : x[k + cnt / 2], keep = upper ? x[k + cnt / 2] : x[k];
+      x[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
   }
+  for (; o > 0; o >>= 1) x[0] += __shfl_xor_sync(0xffffffffu, x[0], o);
+  // lanes that differ only in the bits below the last exchange hold the same sum: the lowest of them stores it
+  constexpr int kSteps = KP == 1 ? 0 : KP == 2 ? 1 : KP == 4 ? 2 : KP == 8 ? 3 : 4;
+  if ((lane & ((32 >> kSteps) - 1)) == 0 && comp < K) s_part[warp][comp] = x[0];
   __syncthreads();
-  if (warp < K) {   // warp k adds the 32 warp sums of component k (xor tree again)
-    double x = s_part[lane][warp];
+  if (warp < K) {   // warp k adds the 32 warp sums of component k
+    double y = s_part[lane][warp];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    if (lane == 0) s_out[warp] = x;
+    for (int q = 16; q > 0; q >>= 1) y += __shfl_xor_sync(0xffffffffu, y, q);
+    if (!PUSH) { if (lane == 0) s_out[warp] = y; }
+    else {
+      // s_out = this CTA's row of the cluster's table [rank][16]: lane r stores the sum into the same row of rank r's table
+      // (distributed shared memory); the caller's cluster barrier publishes it
+      namespace cg = cooperative_groups;
+      cg::cluster_group cluster = cg::this_cluster();
+      if (lane < (int)cluster.num_blocks()) cluster.map_shared_rank(s_out, lane)[warp] = y;
+    }
   }
-  __syncthreads();
+  if (!PUSH) __syncthreads();
 }
 
 __device__ __forceinline__ int cell_coord(float p, float lo, float inv_h, int n) {
@@ -458,23 +482,23 @@ struct OwnStream {
 };
 
 // Sum of K doubles over every thread of the CTAs that share a pair. CL = false: one CTA, block_sum. CL = true: the
-// CTAs of a thread-block cluster; every CTA leaves its block sums in its own shared memory (`s_loc`), and after one
-// cluster barrier every CTA adds the C block sums up in rank order through distributed shared memory — the same total,
-// bit for bit, in every CTA, so nothing has to be broadcast back. `s_loc` alternates between two buffers from one call
-// to the next: the barrier of call k + 1 proves that every CTA has finished reading the buffer of call k.
+// CTAs of a thread-block cluster; every CTA PUSHES its block sums into row `rank` of a table in every CTA's shared
+// memory (distributed shared memory stores), and after one cluster barrier every CTA adds the C rows up in rank order
+// from its own copy — the same total, bit for bit, in every CTA, so nothing has to be broadcast back and nobody waits
+// for a remote load. `s_tab` alternates between two tables from one call to the next: a CTA writes table b again only
+// after the barrier of the call in between, which every CTA reaches after it has read table b.
 template <int K, bool CL>
-__device__ void pair_sum(double (&v)[K], double (*s_part)[16], double* s_loc, double* s_out) {
+__device__ void pair_sum(double (&v)[K], double (*s_part)[16], double (*s_tab)[16], double* s_out) {
   if (!CL) { block_sum<K>(v, s_part, s_out); return; }
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
-  block_sum<K>(v, s_part, s_loc);
+  block_sum<K, true>(v, s_part, s_tab[cluster.block_rank()]);
   cluster.sync();
-  if ((threadIdx.x >> 5) < K) {   // warp k fetches sum k of every rank at once (one remote load per lane), then adds in rank order
-    const unsigned C = cluster.num_blocks(), lane = threadIdx.x & 31, k = threadIdx.x >> 5;
-    const double mine = lane < C ? cluster.map_shared_rank(s_loc, lane)[k] : 0.0;
+  if (threadIdx.x < K) {
     double x = 0.0;
-    for (unsigned r = 0; r < C; ++r) x += __shfl_sync(0xffffffffu, mine, r);
-    if (lane == 0) s_out[k] = x;
+    const unsigned C = cluster.num_blocks();
+    for (unsigned r = 0; r < C; ++r) x += s_tab[r][threadIdx.x];
+    s_out[threadIdx.x] = x;
   }
   __syncthreads();
 }
@@ -491,7 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
   __shared__ float s_red[kWarps];
   __shared__ float s_rmax;
   __shared__ double s_sum[16];
-  __shared__ double s_loc[2][16];
+  __shared__ double s_tab[2][16][16];   // pair_sum: [call parity][rank][component]
   extern __shared__ float4 s_ring[];   // kRingBytes: the passes' cp.async rings (OwnStream)
   __shared__ float s_T[16];
   __shared__ double s_V[9];   // right singular vectors of the last solve (thread 0)
@@ -683,7 +707,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
     double a4[4];
     for (int k = 0; k < 4; ++k) a4[k] = isfinite(h4[k]) ? (double)h4[k] + (double)l4[k] : (double)h4[k];   // inf - inf in lo otherwise
     PHASE(4);
-    pair_sum<4, CL>(a4, s_part, s_loc[0], s_sum);
+    pair_sum<4, CL>(a4, s_part, s_tab[0], s_sum);
     PHASE(5);
     cost = s_sum[0];
     float dmean[3];
@@ -712,7 +736,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
     double cv[9];
     for (int k = 0; k < 9; ++k) cv[k] = isfinite(hv[k]) ? (double)hv[k] + (double)lv[k] : (double)hv[k];
     PHASE(6);
-    pair_sum<9, CL>(cv, s_part, s_loc[1], s_sum);
+    pair_sum<9, CL>(cv, s_part, s_tab[1], s_sum);
     PHASE(5);
     // ---- closed-form pose (:139-151); in a cluster every CTA solves from the same totals (no broadcast)
     if (tid == 0) {
