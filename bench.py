@@ -601,6 +601,16 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                 okr, Tr, mcr, cnts = al.icp3d_depth(frames, sidx, didx, intr)
             dtr = (time.perf_counter() - t0r) / reps
             rerr = np.array([synth.pose_error(Tr[i], gt[i]) for i in range(n_pairs)])
+            searched, queried = al.icp3d_cache_stats()
+            al.set_icp3d_cache(0.0, 0.0, 0.0)                              # every point searches in every iteration
+            t0n = time.perf_counter()
+            okn, Tn_, _, _ = al.icp3d_depth(frames, sidx, didx, intr)
+            dt_nocache = time.perf_counter() - t0n
+            al.set_icp3d_cache()
+            cache = {"searched": searched, "queried": queried, "searched_fraction": searched / max(queried, 1),
+                     "without_cache_pairs_per_s": n_pairs / dt_nocache, "poses_bit_identical_to_without_cache": bool(np.array_equal(Tn_, Tr)),
+                     "what": "a query searches only when |p' - nbr| + (motion since the entry was proven) >= the proven radius (triangle inequality); "
+                             "indices and distances are those of a search, bit for bit"}
             # one pair at a time, as the reference's caller runs it (rs_replay_app.cpp:246-251): one CTA per pair vs the
             # automatic thread-block cluster per pair
             single = {}
@@ -614,7 +624,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             al.set_icp3d_cluster(0)
             ref_gpu = {"value": n_pairs / dtr, "single_pair": single, "unit": "pairs/s", "ms_per_step": dtr * 1e3, "timing": "host wall clock, H2D + D2H included",
                        "algorithm": "reference AlignIcp3d on the GPU: exact grid NN, GM/GNC weights, Kabsch, 128 iterations, voxel 0.05",
-                       "mean_cloud_points": float(np.mean(cnts)), "pairs_ok": int(okr.sum()),
+                       "mean_cloud_points": float(np.mean(cnts)), "pairs_ok": int(okr.sum()), "neighbour_cache": cache,
                        "pose_err_vs_gt": {"t_m_max": float(rerr[:, 0].max()), "r_rad_max": float(rerr[:, 1].max())}}
         h2d = FRAMES * H * W * 2 + n_pairs * (8 + 64)
         d2h = n_pairs * (64 + C.sizeof(N.Stats))

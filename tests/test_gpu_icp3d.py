@@ -220,3 +220,38 @@ def test_neighbour_cache_changes_nothing_but_time(al):
     finally:
         al.set_icp3d_cluster(0)
         al.set_icp3d_cache()
+
+
+def test_neighbour_cache_ties_long_runs_and_large_motion(al):
+    """The cases the cache has to get right by NOT skipping: duplicated target points (ties go to the lowest index, the
+    runner-up distance equals the best), 300 iterations (the iteration tag of a cache entry wraps at 256; entries older
+    than 250 iterations search again), an initial misalignment of 20 cm / 12 degrees (every early iteration moves every
+    point further than its proven radius), a ragged source size — each bit-identical to searching every time."""
+    rng = np.random.default_rng(7)
+    src, dst = depth_clouds(1, 0)
+    dst_dup = np.concatenate([dst, dst[::3], dst[::7]]).astype(np.float32)           # exact duplicates, higher indices
+    T_far = synth.make_pose(synth.rotvec_to_R([0.12, -0.15, 0.08]), [0.2, -0.1, 0.15])
+    cases = [(src[:4001], dst_dup, np.eye(4), 64), (src, dst, T_far, 128), (src[:1500], dst, np.eye(4), 300),
+             ((rng.random((3000, 3)) * 2 - 1).astype(np.float32), (rng.random((2500, 3)) * 2 - 1).astype(np.float32), np.eye(4), 40)]
+    try:
+        for cl in (1, 8):
+            al.set_icp3d_cluster(cl)
+            for s_, d_, T0, it in cases:
+                al.set_icp3d_cache(0.0, 0.0, 0.0)
+                ok0, Ta, ex0 = al.icp3d_pairs([s_], [d_], it, T0=T0, details=True)
+                searched0, queried0 = al.icp3d_cache_stats()
+                assert queried0 == len(s_) * it and searched0 == queried0
+                al.set_icp3d_cache()
+                ok1, Tb, ex1 = al.icp3d_pairs([s_], [d_], it, T0=T0, details=True)
+                searched1, queried1 = al.icp3d_cache_stats()
+                assert queried1 == queried0 and len(s_) <= searched1 <= queried1
+                assert np.array_equal(Ta, Tb) and ok0[0] == ok1[0], (cl, it)
+                assert np.array_equal(ex0[0]["nbrs"], ex1[0]["nbrs"]) and np.array_equal(ex0[0]["weights"], ex1[0]["weights"])
+                assert np.array_equal(ex0[0]["cov"], ex1[0]["cov"]) and ex0[0]["mean_cost"] == ex1[0]["mean_cost"]
+        # duplicates: the reported neighbour is the lowest index among the tied points
+        ok, T, ex = al.icp3d_pairs([src[:4001]], [dst_dup], 3, details=True)
+        first_of = {tuple(p): i for i, p in reversed(list(enumerate(map(tuple, dst_dup))))}
+        assert all(first_of[tuple(dst_dup[j])] == j for j in ex[0]["nbrs"])
+    finally:
+        al.set_icp3d_cluster(0)
+        al.set_icp3d_cache()
