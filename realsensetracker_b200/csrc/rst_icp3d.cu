@@ -679,8 +679,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
       xform(T, a.x, a.y, a.z, px, py, pz);
       int cand, j;
       float d2, L, margin = cache.y * g.h;
-      if (iter == 0) nn_search(g, P.cell_start, P.sorted, px, py, pz, &cand, &d2);
-      else {
+      if (iter == 0) {
+        // any target point is a valid candidate for the ball scan; one from the query's own cell makes the ball small
+        // (a few cells instead of the 27 of a ring search). An empty cell falls back to the ring search.
+        const int c = (cell_coord(pz, g.loz, g.inv_h, g.nz) * g.ny + cell_coord(py, g.loy, g.inv_h, g.ny)) * g.nx + cell_coord(px, g.lox, g.inv_h, g.nx);
+        const int k0 = P.cell_start[c];
+        if (k0 < P.cell_start[c + 1]) cand = __float_as_int(P.sorted[k0].w);
+        else nn_search(g, P.cell_start, P.sorted, px, py, pz, &cand, &d2);
+      } else {
         cand = P.nbr[i];
         margin = fminf(fmaxf(cache.x * (moved_now - s_cum[__float_as_int(a.w) & 255]), margin), cache.z * g.h);
       }
@@ -693,19 +699,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
     PHASE(3);
     if (tid == 0) s_qn = 0;   // every thread has read qn; visible to the next iteration through pair_sum's barriers
     // C: cost and the neighbour sum in the fixed per-thread order (four points per trip)
-    float h4[4] = {0, 0, 0, 0}, l4[4] = {0, 0, 0, 0};  // cost, sum dst_j (hi, lo)
+    // (four sums: the conversion pipe keeps up with a float -> double conversion per term here; the nine covariance
+    // sums below would saturate it and are kept as compensated fp32 pairs instead)
+    double a4[4] = {0, 0, 0, 0};  // cost, sum dst_j
     {
       OwnStream<1> in{s_ring, {P.qd}, first, stride, P.n};
       in.start();
       for (int trip = 0, i = first; i < P.n; ++trip, i += stride) {
         float4 b[1];
         in.get(trip, b);
-        acc2(h4[0], l4[0], b[0].w); acc2(h4[1], l4[1], b[0].x); acc2(h4[2], l4[2], b[0].y); acc2(h4[3], l4[3], b[0].z);
+        a4[0] += (double)b[0].w; a4[1] += (double)b[0].x; a4[2] += (double)b[0].y; a4[3] += (double)b[0].z;
       }
       in.finish();
     }
-    double a4[4];
-    for (int k = 0; k < 4; ++k) a4[k] = isfinite(h4[k]) ? (double)h4[k] + (double)l4[k] : (double)h4[k];   // inf - inf in lo otherwise
     PHASE(4);
     pair_sum<4, CL>(a4, s_part, s_tab[0], s_sum);
     PHASE(5);
