@@ -358,7 +358,7 @@ int32_t rst_set_icp3d_cluster(rst_ctx* ctx, int32_t ctas_per_pair);
  * inequality |p' - nbr| + |p' - p| < L shows, for most points, that the neighbour cannot have changed, and the search is
  * skipped. The neighbour index and its fp32 squared distance are the ones a search would return, bit for bit — only
  * the time changes. margin = clamp(gain * motion of the point since its last search, lo_cells * cell, hi_cells * cell).
- * hi_cells = 0 switches the cache off (every point searches in every iteration). Defaults: 4, 0.05, 0.5. */
+ * hi_cells = 0 switches the cache off (every point searches in every iteration). Defaults: 1, 0.05, 0.2. */
 int32_t rst_set_icp3d_cache(rst_ctx* ctx, float gain, float lo_cells, float hi_cells);
 
 /* Of the last rst_icp3d_pairs / rst_icp3d_depth call of this context: how many neighbour queries were answered

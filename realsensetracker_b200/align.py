@@ -340,7 +340,7 @@ class Aligner:
         """CTAs per pair of the cloud ICP kernel: 0 = automatic, or 1 / 2 / 4 / 8 / 16."""
         self._check(self._lib.rst_set_icp3d_cluster(self._ctx, ctas_per_pair))
 
-    def set_icp3d_cache(self, gain: float = 4.0, lo_cells: float = 0.05, hi_cells: float = 0.5):
+    def set_icp3d_cache(self, gain: float = 1.0, lo_cells: float = 0.05, hi_cells: float = 0.2):
         """Neighbour cache of the cloud ICP kernel (scan margin = clamp(gain * motion, lo, hi) in grid cells); hi_cells = 0: off."""
         self._check(self._lib.rst_set_icp3d_cache(self._ctx, gain, lo_cells, hi_cells))
 

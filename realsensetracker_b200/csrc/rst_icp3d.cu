@@ -42,7 +42,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kCellCap = 1 << 18;  // grid cells per pair (1 MiB of cell_start)
 constexpr int kRingBytes = 8 * kThreads * 16;   // dynamic shared memory of k_icp3d (OwnStream)
 constexpr int kGroupScanMax = 2048;   // queued points per CTA up to which a search is spread over kScanLanes lanes
-constexpr float kCacheGain = 4.0f, kCacheLo = 0.05f, kCacheHi = 0.5f;   // neighbour-cache scan margin (see nn_ball)
+constexpr float kCacheGain = 1.0f, kCacheLo = 0.05f, kCacheHi = 0.2f;   // neighbour-cache scan margin (see nn_ball)
 
 struct PairDesc {
   const float* src;   // n x 3

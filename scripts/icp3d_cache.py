@@ -15,7 +15,7 @@ _, gt = synth.render_sequence(n, W, H, seed=0, pinned=frames)
 al = Aligner(16, 16, 2, 1)
 s, d = np.arange(1, n, dtype=np.int32), np.arange(0, n - 1, dtype=np.int32)
 al.icp3d_depth(frames, s, d, intr, max_iter=1)
-settings = [(0, 0, 0), (4, 0.05, 0.5), (2, 0.05, 0.5), (1, 0.05, 0.5), (2, 0.02, 0.25), (0, 0.05, 0.05)]
+settings = [(0, 0, 0), (1, 0.05, 0.2), (4, 0.05, 0.5), (2, 0.1, 0.3), (0, 0.05, 0.05)]
 if len(sys.argv) > 1:
     settings = [(0, 0, 0)] + [tuple(float(x) for x in a.split(",")) for a in sys.argv[1:]]
 base = None

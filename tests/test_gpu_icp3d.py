@@ -207,7 +207,7 @@ def test_neighbour_cache_changes_nothing_but_time(al):
             al.set_icp3d_cluster(cl)
             al.set_icp3d_cache(0.0, 0.0, 0.0)
             ok0, Ta, ex0 = al.icp3d_pairs([src, src2], [dst, dst2], 128, T0=T0, details=True)
-            for setting in ((4.0, 0.05, 0.5), (0.0, 0.0, 0.01), (8.0, 0.5, 2.0)):
+            for setting in ((1.0, 0.05, 0.2), (4.0, 0.05, 0.5), (0.0, 0.0, 0.01), (8.0, 0.5, 2.0)):
                 al.set_icp3d_cache(*setting)
                 for cell in (0.1, 0.0):
                     ok1, Tb, ex1 = al.icp3d_pairs([src, src2], [dst, dst2], 128, T0=T0, grid_cell=cell, details=True)
