@@ -41,6 +41,7 @@ constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
 constexpr int kCellCap = 1 << 18;  // grid cells per pair (1 MiB of cell_start)
 constexpr int kRingBytes = 8 * kThreads * 16;   // dynamic shared memory of k_icp3d (OwnStream)
+constexpr int kUploadChunks = 4;   // rst_icp3d_depth: frame upload / depth -> cloud pipeline depth
 constexpr int kGroupScanMax = 2048;   // queued points per CTA up to which a search is spread over kScanLanes lanes
 constexpr float kCacheGain = 1.0f, kCacheLo = 0.05f, kCacheHi = 0.2f;   // neighbour-cache scan margin (see nn_ball)
 
@@ -1443,6 +1444,10 @@ struct Icp3dState {
   // neighbour cache of k_icp3d: scan margin = clamp(x * motion since the last scan, y * cell, z * cell); z <= 0 = off
   float3 cache = make_float3(kCacheGain, kCacheLo, kCacheHi);
   unsigned long long searched = 0, queried = 0;   // of the last rst_icp3d_pairs / rst_icp3d_depth call
+  // rst_icp3d_depth uploads its frames in chunks on a stream of its own, the depth -> cloud kernels of a chunk waiting
+  // for that chunk only
+  cudaStream_t copy = nullptr;
+  cudaEvent_t ev[kUploadChunks + 1] = {};
 };
 
 inline void sum_stats(Icp3dState* st, const unsigned long long* s, int n_pairs) {
@@ -1452,6 +1457,8 @@ inline void sum_stats(Icp3dState* st, const unsigned long long* s, int n_pairs) 
 
 void icp3d_free(void* p) {
   Icp3dState* s = static_cast<Icp3dState*>(p);
+  if (s->copy) cudaStreamDestroy(s->copy);
+  for (cudaEvent_t e : s->ev) if (e) cudaEventDestroy(e);
   cudaFree(s->d_arena);
   cudaFreeHost(s->h_arena);
   delete s;
@@ -1705,21 +1712,37 @@ extern "C" int32_t rst_icp3d_depth(rst_ctx* c, const rst_frame* frames, int32_t 
   }
   if (n_pairs > 0) std::memcpy(H + o_pose, poses_inout, sizeof(float) * 16 * n_pairs);
   ICP_CUDA(cudaMemcpyAsync(D, H, upload_bytes, cudaMemcpyHostToDevice, stream));
-  for (int f = 0; f < n_frames; ++f)
-    ICP_CUDA(cudaMemcpy2DAsync(D + o_depth + npx * 2 * f, (size_t)w * 2, frames[f].depth, (size_t)frames[f].depth_stride_bytes,
-                               (size_t)w * 2, (size_t)h, cudaMemcpyHostToDevice, stream));
+  // frames go up in chunks on the copy stream; the depth -> cloud kernels of chunk k run under the copy of chunk k + 1
+  const int n_chunks = n_frames >= 4 * kUploadChunks ? kUploadChunks : 1;
+  if (n_chunks > 1 && !st->copy) {
+    ICP_CUDA(cudaStreamCreateWithFlags(&st->copy, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : st->ev) ICP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  if (n_chunks > 1) {   // the arena may still be read by this stream's earlier work
+    ICP_CUDA(cudaEventRecord(st->ev[kUploadChunks], stream));
+    ICP_CUDA(cudaStreamWaitEvent(st->copy, st->ev[kUploadChunks], 0));
+  }
   if (decimate) {
     ICP_CUDA(cudaMemsetAsync(D + o_keys, 0, (size_t)cap * 8 * n_frames, stream));
     ICP_CUDA(cudaMemsetAsync(D + o_vals, 0x7f, (size_t)cap * 4 * n_frames, stream));  // 0x7f7f7f7f > any pixel index
   }
   ICP_CUDA(cudaMemsetAsync(D + o_res, 0, sizeof(rst_icp3d_result) * (size_t)(n_pairs > 0 ? n_pairs : 1), stream));
   ICP_CUDA(cudaMemsetAsync(D + o_stat, 0, sizeof(unsigned long long) * 2 * (size_t)(n_pairs > 0 ? n_pairs : 1), stream));
-  {
-    const CloudifyDesc* dd = reinterpret_cast<const CloudifyDesc*>(D + o_cdesc);
-    const dim3 gpx((unsigned)((npx + 255) / 256), n_frames), gseg(n_seg, n_frames);
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int f0 = (int)((long long)n_frames * ch / n_chunks), f1 = (int)((long long)n_frames * (ch + 1) / n_chunks), nf = f1 - f0;
+    cudaStream_t up = n_chunks > 1 ? st->copy : stream;
+    for (int f = f0; f < f1; ++f)
+      ICP_CUDA(cudaMemcpy2DAsync(D + o_depth + npx * 2 * f, (size_t)w * 2, frames[f].depth, (size_t)frames[f].depth_stride_bytes,
+                                 (size_t)w * 2, (size_t)h, cudaMemcpyHostToDevice, up));
+    if (n_chunks > 1) {
+      ICP_CUDA(cudaEventRecord(st->ev[ch], st->copy));
+      ICP_CUDA(cudaStreamWaitEvent(stream, st->ev[ch], 0));
+    }
+    const CloudifyDesc* dd = reinterpret_cast<const CloudifyDesc*>(D + o_cdesc) + f0;
+    const dim3 gpx((unsigned)((npx + 255) / 256), nf), gseg(n_seg, nf);
     if (decimate) k_cloudify_insert<<<gpx, 256, 0, stream>>>(dd, w, h, intr->fx, intr->fy, intr->cx, intr->cy, depth_scale, voxel, cap - 1);
     k_cloudify_segment<false><<<gseg, kSegThreads, 0, stream>>>(dd, w, h, intr->fx, intr->fy, intr->cx, intr->cy, depth_scale, voxel, cap - 1);
-    k_cloudify_scan<<<n_frames, kThreads, 0, stream>>>(dd, n_seg);
+    k_cloudify_scan<<<nf, kThreads, 0, stream>>>(dd, n_seg);
     k_cloudify_segment<true><<<gseg, kSegThreads, 0, stream>>>(dd, w, h, intr->fx, intr->fy, intr->cx, intr->cy, depth_scale, voxel, cap - 1);
     ICP_CUDA(cudaGetLastError());
     rst::ctx_count_launches(c, decimate ? 4 : 3);
