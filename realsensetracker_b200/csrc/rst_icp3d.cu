@@ -35,6 +35,14 @@
 #define PHASE(k) do { } while (0)
 #endif
 
+// -DRST_ICP3D_CHECK: index checks in k_icp3d that trap (compute-sanitizer is not available on the GPU pool; the tests are
+// run once against a library built this way)
+#ifdef RST_ICP3D_CHECK
+#define ICP3D_CHECK(cond) do { if (!(cond)) { printf("k_icp3d check failed: %s (line %d)\n", #cond, __LINE__); __trap(); } } while (0)
+#else
+#define ICP3D_CHECK(cond) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kThreads = 1024;
@@ -292,6 +300,7 @@ __device__ void nn_ball(const Grid& g, const int* __restrict__ cell_start, const
     for (int y = y0; y <= y1; ++y) {
       const int row = (z * g.ny + y) * g.nx;
       // the cells x0..x1 of one row are contiguous in the sorted array: one range instead of x1-x0+1
+      ICP3D_CHECK(row + x0 >= 0 && x0 <= x1 && row + x1 + 1 <= g.nx * g.ny * g.nz);
       const int e = cell_start[row + x1 + 1];
       for (int k = cell_start[row + x0]; k < e; ++k) {
         const float4 q = sorted[k];
@@ -329,6 +338,7 @@ __device__ void nn_ball_group(const Grid& g, const int* __restrict__ cell_start,
     const int ny = y1 - y0 + 1, rows = ny * (z1 - z0 + 1);
     for (int r = threadIdx.x & (kScanLanes - 1); r < rows; r += kScanLanes) {
       const int row = ((z0 + r / ny) * g.ny + y0 + r % ny) * g.nx;
+      ICP3D_CHECK(row + x0 >= 0 && x0 <= x1 && row + x1 + 1 <= g.nx * g.ny * g.nz);
       const int e = cell_start[row + x1 + 1];
       for (int k = cell_start[row + x0]; k < e; ++k) {
         const float4 q = sorted[k];
@@ -634,7 +644,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
         const float m = __int_as_float(__float_as_int(a.w) & ~255) - (moved_now - s_cum[(iter - age) & 255]);   // L - motion since L was proven
         if (m > 0.f && d2c * 1.0005f < m * m) { P.qd[i].w = d2c; return; }   // |p - nbr| + motion < L: proven, nbr stays
       }
-      queue[atomicAdd(&s_qn, 1)] = i;
+      const int slot = atomicAdd(&s_qn, 1);
+      ICP3D_CHECK(slot < (CL ? P.n / (int)cg::this_cluster().num_blocks() + kThreads : P.n));
+      queue[slot] = i;
     };
     {
       OwnStream<2> in{s_ring, {P.sl, P.qd}, first, stride, P.n};
@@ -665,7 +677,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
         const float margin = fminf(fmaxf(cache.x * (moved_now - s_cum[__float_as_int(a.w) & 255]), cache.y * g.h), cache.z * g.h);
         int j;
         float d2, L;
+        ICP3D_CHECK(i >= 0 && i < P.n && cand >= 0 && cand < P.m);
         nn_ball_group(g, P.cell_start, P.sorted, P.dst, active, px, py, pz, cand, cache_on ? margin : 0.f, &j, &d2, &L);
+        ICP3D_CHECK(!active || (j >= 0 && j < P.m));
         if (active && (tid & (kScanLanes - 1)) == 0) {
           P.nbr[i] = j;
           P.sl[i].w = __int_as_float((__float_as_int(L) & ~255) | (iter & 255));
@@ -691,7 +705,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
         cand = P.nbr[i];
         margin = fminf(fmaxf(cache.x * (moved_now - s_cum[__float_as_int(a.w) & 255]), margin), cache.z * g.h);
       }
+      ICP3D_CHECK(i >= 0 && i < P.n && cand >= 0 && cand < P.m);
       nn_ball(g, P.cell_start, P.sorted, P.dst, px, py, pz, cand, cache_on ? margin : 0.f, &j, &d2, &L);
+      ICP3D_CHECK(j >= 0 && j < P.m);
       P.nbr[i] = j;
       P.sl[i].w = __int_as_float((__float_as_int(L) & ~255) | (iter & 255));   // L rounded down, tagged with this iteration
       P.qd[i] = make_float4(P.dst[3 * j], P.dst[3 * j + 1], P.dst[3 * j + 2], d2);

@@ -135,6 +135,20 @@ def test_solve_kabsch_on_the_device(al):
         assert synth.pose_error(T_g, GOLD["T_big"]) < (1e-4, 1e-4)          # the known rotation of rs_align_app.cpp:257-263
     ok_g, _ = al.solve_kabsch(src[:2], dst, pairs[:1] * 0)
     assert ok_g is False                                                     # < 3 points (:23-25)
+    # the device SVD (division-free one-sided Jacobi) against LAPACK, not against an oracle that shares its algorithm:
+    # R = U V^T of the fp64 cross-covariance by numpy.linalg.svd, for well- and ill-conditioned (nearly planar) sets
+    for flat in (1.0, 1e-3):
+        s2 = (rng.standard_normal((500, 3)) * [1.0, 0.7, flat]).astype(np.float32)
+        R_true = synth.rotvec_to_R([0.4, -0.9, 0.3])
+        d2 = (s2 @ R_true.T.astype(np.float32) + np.float32([0.3, -0.2, 1.1])).astype(np.float32)
+        pr = np.stack([np.arange(500), np.arange(500)], 1)
+        ok_g, T_g = al.solve_kabsch(s2, d2, pr)
+        sm, dm = s2.mean(0, dtype=np.float64).astype(np.float32), d2.mean(0, dtype=np.float64).astype(np.float32)
+        cov = ((d2 - dm)[:, :, None] * (s2 - sm)[:, None, :]).astype(np.float32).astype(np.float64).sum(0)
+        U, _, Vt = np.linalg.svd(cov)
+        R_np = U @ Vt
+        assert ok_g and np.abs(T_g[:3, :3] - R_np).max() < 2e-6, (flat, np.abs(T_g[:3, :3] - R_np).max())
+        assert np.abs(T_g[:3, :3] - R_true).max() < (2e-6 if flat == 1.0 else 2e-3)
     # Kabsch initialiser -> AlignIcp3d, the order rs_align_app.cpp:295-303 uses
     ok_k, T_k = al.solve_kabsch(src, dst, pairs)
     ok_i, T_i = al.icp3d_pairs([src], [dst], 16, T0=T_k)
