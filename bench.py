@@ -622,9 +622,28 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                     al.icp3d_depth(frames[:2], sidx[:1], didx[:1], intr)
                 single[name + "_ms"] = (time.perf_counter() - t0s) / 10 * 1e3
             al.set_icp3d_cluster(0)
+            # the cloud utilities and the GICP alignment of the reference's align library on one pair's clouds
+            # (host clouds in, results out, best of 5 blocking calls each)
+            src_c, dst_c = al.icp3d_read_cloud(1, int(cnts[1])), al.icp3d_read_cloud(0, int(cnts[0]))
+
+            def best_ms(f, reps=5):
+                f()
+                best = 1e9
+                for _ in range(reps):
+                    t0u = time.perf_counter(); f(); best = min(best, time.perf_counter() - t0u)
+                return best * 1e3
+            utils = {"points": [int(len(src_c)), int(len(dst_c))],
+                     "find_correspondences_ms": best_ms(lambda: al.find_correspondences(dst_c, src_c)),
+                     "compute_normals_k16_ms": best_ms(lambda: al.cloud_normals(src_c, k=16)),
+                     "compute_covariances_ms": best_ms(lambda: al.cloud_covariances(src_c)),
+                     "downsample_voxel_ms": best_ms(lambda: al.downsample_voxel(src_c, 0.1)),
+                     "align_icp3d_128it_ms": best_ms(lambda: al.icp3d_pairs([src_c], [dst_c], 128)),
+                     "gicp_align_16x4_ms": best_ms(lambda: al.gicp_align(src_c, dst_c))}
+            Tg_, _ = al.gicp_align(src_c, dst_c)
+            utils["gicp_pose_err_vs_gt_t_m"] = float(synth.pose_error(Tg_, gt[0])[0])
             ref_gpu = {"value": n_pairs / dtr, "single_pair": single, "unit": "pairs/s", "ms_per_step": dtr * 1e3, "timing": "host wall clock, H2D + D2H included",
                        "algorithm": "reference AlignIcp3d on the GPU: exact grid NN, GM/GNC weights, Kabsch, 128 iterations, voxel 0.05",
-                       "mean_cloud_points": float(np.mean(cnts)), "pairs_ok": int(okr.sum()), "neighbour_cache": cache,
+                       "mean_cloud_points": float(np.mean(cnts)), "pairs_ok": int(okr.sum()), "neighbour_cache": cache, "cloud_utilities": utils,
                        "pose_err_vs_gt": {"t_m_max": float(rerr[:, 0].max()), "r_rad_max": float(rerr[:, 1].max())}}
         h2d = FRAMES * H * W * 2 + n_pairs * (8 + 64)
         d2h = n_pairs * (64 + C.sizeof(N.Stats))
