@@ -8,7 +8,11 @@
  * __syncthreads), so a batch of pairs is one kernel launch and there is no host round trip per
  * iteration. The KD-tree (nanoflann, kdtree.hpp:27-57) is replaced by a uniform grid over the dst
  * cloud built in the same kernel, searched in growing rings until the ring bound proves the current
- * best is the exact nearest neighbour (ties: lowest index).
+ * best is the exact nearest neighbour (ties: lowest index). From the second iteration on a query searches only
+ * the ball through its previous neighbour — and not at all while the triangle inequality proves that neighbour
+ * cannot have changed (the neighbour cache, see nn_ball): the result of every query is the one a search would
+ * return, index and fp32 distance, bit for bit. A small batch gives every pair a thread-block cluster instead of
+ * one CTA (sums through distributed shared memory).
  *
  * fp32 arithmetic that decides a neighbour (transform, squared distance) uses explicit
  * round-to-nearest intrinsics in the reference's operation order (no FMA contraction), so NN indices
