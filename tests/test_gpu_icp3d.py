@@ -246,6 +246,8 @@ def test_neighbour_cache_ties_long_runs_and_large_motion(al):
     dst_dup = np.concatenate([dst, dst[::3], dst[::7]]).astype(np.float32)           # exact duplicates, higher indices
     T_far = synth.make_pose(synth.rotvec_to_R([0.12, -0.15, 0.08]), [0.2, -0.1, 0.15])
     cases = [(src[:4001], dst_dup, np.eye(4), 64), (src, dst, T_far, 128), (src[:1500], dst, np.eye(4), 300),
+             (src[:5], dst, np.eye(4), 10), (src[:1025], dst[:50], np.eye(4), 20),      # CTAs of a cluster without a point; tiny target
+
              ((rng.random((3000, 3)) * 2 - 1).astype(np.float32), (rng.random((2500, 3)) * 2 - 1).astype(np.float32), np.eye(4), 40)]
     try:
         for cl in (1, 8):
