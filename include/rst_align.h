@@ -365,6 +365,16 @@ int32_t rst_set_icp3d_cache(rst_ctx* ctx, float gain, float lo_cells, float hi_c
  * (source points x iterations, over all pairs) and how many of them had to search (the rest were proven by the cache). */
 int32_t rst_icp3d_cache_stats(rst_ctx* ctx, uint64_t* searched_out, uint64_t* queried_out);
 
+/* Fixed-point skip of the cloud ICP kernel (default on). The reference runs max_iter iterations whatever happens
+ * (align_icp.cpp:92-153). Once an iteration returns the pose it was given, bit for bit, the iterations after it repeat it
+ * exactly until mu changes (every 8th iteration, :96-98): same pose in, same neighbours, same sums, same pose out. The
+ * kernel detects that state (pose unchanged AND its SVD warm-start basis unchanged, i.e. the complete state an
+ * iteration depends on) and continues at the next change of mu; the last iteration is always run. Results are those of
+ * running every iteration, bit for bit (test); rst_icp3d_result.iterations still reports max_iter. on = 0 runs them all.
+ * rst_icp3d_iteration_stats: iterations actually run / asked for, summed over the pairs of the last call. */
+int32_t rst_set_icp3d_fixed_point_skip(rst_ctx* ctx, int32_t on);
+int32_t rst_icp3d_iteration_stats(rst_ctx* ctx, uint64_t* run_out, uint64_t* asked_out);
+
 /* bool SolveKabsch(src, dst, indices, weights, &xfm)  (align_icp.hpp:14-18, align_icp.cpp:18-71) on the device:
  * closed-form pose from GIVEN (src index, dst index) pairs — the initialiser rs_align_app.cpp:295 feeds to
  * AlignIcp3d. `pairs`: n_pairs x 2 int32; `weights`: n_pairs floats or NULL (the reference's empty vector);

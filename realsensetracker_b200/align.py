@@ -344,6 +344,16 @@ class Aligner:
         """Neighbour cache of the cloud ICP kernel (scan margin = clamp(gain * motion, lo, hi) in grid cells); hi_cells = 0: off."""
         self._check(self._lib.rst_set_icp3d_cache(self._ctx, gain, lo_cells, hi_cells))
 
+    def set_icp3d_fixed_point_skip(self, on: bool = True):
+        """Cloud ICP: jump over iterations that provably repeat the previous one (default on; results unchanged)."""
+        self._check(self._lib.rst_set_icp3d_fixed_point_skip(self._ctx, 1 if on else 0))
+
+    def icp3d_iteration_stats(self):
+        """(iterations run, iterations asked for) summed over the pairs of the last cloud-ICP call."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._lib.rst_icp3d_iteration_stats(self._ctx, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def icp3d_cache_stats(self):
         """(neighbour queries that searched, neighbour queries answered) of the last cloud-ICP call."""
         a, b = C.c_uint64(0), C.c_uint64(0)

@@ -71,7 +71,7 @@ struct PairDesc {
   float4* sl;         // n   (source point, neighbour cache: proven radius L | iteration tag)
   float4* qd;         // n   (coordinates of the current neighbour, squared distance to it)
   int* queue;         // n + 16 * kThreads: source points whose neighbour has to be searched this iteration
-  unsigned long long* stat;   // [2]: neighbour searches done, neighbour queries answered (zeroed by the host)
+  unsigned long long* stat;   // [4]: neighbour searches done, neighbour queries answered, iterations run, iterations asked (zeroed by the host)
   float* pose;        // 16, column-major, in/out
   rst_icp3d_result* res;
 };
@@ -375,10 +375,11 @@ __device__ void nn_ball_group(const Grid& g, const int* __restrict__ cell_start,
 // without a division or a square root: with tau = beta - alpha, kappa = 2 gamma, rho = |(tau, kappa)|,
 //   c = (|tau| + rho) / sqrt(2 rho (rho + |tau|)),  s = sign(tau) kappa / sqrt(2 rho (rho + |tau|))
 // (the same angle as t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = tau / kappa), two reciprocal square roots.
-__device__ void svd_uvt(const double* M, double* UVt, double* V) {
+__device__ bool svd_uvt(const double* M, double* UVt, double* V) {   // returns whether any rotation was applied (V changed)
   double B[9];
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) B[3 * i + j] = M[3 * i] * V[j] + M[3 * i + 1] * V[3 + j] + M[3 * i + 2] * V[6 + j];
+  bool any_rotation = false;
   for (int sweep = 0; sweep < 60; ++sweep) {
     bool rotated = false;
     for (int p = 0; p < 2; ++p)
@@ -399,6 +400,7 @@ __device__ void svd_uvt(const double* M, double* UVt, double* V) {
         }
       }
     if (!rotated) break;
+    any_rotation = true;
   }
   double U[9], s[3], inv[3];
   for (int j = 0; j < 3; ++j) {
@@ -424,6 +426,7 @@ __device__ void svd_uvt(const double* M, double* UVt, double* V) {
       for (int k = 0; k < 3; ++k) acc += U[3 * i + k] * V[3 * j + k];
       UVt[3 * i + j] = acc;
     }
+  return any_rotation;
 }
 
 // xfm = Translation3f{t} * Quaternionf{R} (align_icp.cpp:151), column-major 4x4 out
@@ -521,9 +524,10 @@ __device__ void pair_sum(double (&v)[K], double (*s_part)[16], double (*s_tab)[1
 // grid (n_pairs) [CL = false] or (C, n_pairs) in clusters of (C, 1, 1) [CL = true: the C CTAs split the source points
 // of one pair — small batches, where one CTA per pair would leave most of the 148 SMs idle].
 template <bool CL>
-__global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restrict__ descs, int max_iter, float grid_cell, float3 cache) {
+__global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restrict__ descs, int max_iter, float grid_cell, float3 cache, int skip_fixed) {
   __shared__ double s_part[kWarps][16];
   __shared__ int s_qn;
+  __shared__ int s_next;   // the iteration that follows the current one (thread 0's decision, see the solve)
   // s_cum[k & 255]: upper bound of the path length ANY source point has travelled from the initial pose to the pose of
   // iteration k (sum of per-iteration bounds): a point moved at most s_cum[now] - s_cum[k] since iteration k
   __shared__ float s_cum[256];
@@ -616,7 +620,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
 #ifdef RST_ICP3D_PROFILE
   long long ph_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_ = clock64();
 #endif
-  for (int iter = 0; iter < max_iter; ++iter) {
+  unsigned iters_run = 0;
+  for (int iter = 0; iter < max_iter; iter = s_next) {
+    ++iters_run;
     if (iter > 0 && iter % 8 == 0) mu = __fdiv_rn(mu, 1.4f);  // :96-98
     float T[12];
     T[0] = s_T[0]; T[1] = s_T[1]; T[2] = s_T[2]; T[3] = s_T[4]; T[4] = s_T[5]; T[5] = s_T[6];
@@ -769,7 +775,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
     if (tid == 0) {
       double cov[9], uvt[9];
       for (int k = 0; k < 9; ++k) cov[k] = s_sum[k];
-      svd_uvt(cov, uvt, s_V);   // warm start from the previous iteration's right singular vectors
+      const bool v_moved = svd_uvt(cov, uvt, s_V);   // warm start from the previous iteration's right singular vectors
       float R[9], t[3];
       for (int k = 0; k < 9; ++k) R[k] = (float)uvt[k];
       const float det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) + R[2] * (R[3] * R[7] - R[4] * R[6]);
@@ -784,7 +790,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
         for (int r = 0; r < 3; ++r)
           cm[r] = (Tn[r] - s_T[r]) * smean[0] + (Tn[4 + r] - s_T[4 + r]) * smean[1] + (Tn[8 + r] - s_T[8 + r]) * smean[2] + (Tn[12 + r] - s_T[12 + r]);
         const float step = (sqrtf(f2) * rmax + sqrtf(cm[0] * cm[0] + cm[1] * cm[1] + cm[2] * cm[2])) * 1.001f + 1e-7f * rmax;
-        s_cum[(iter + 1) & 255] = moved_now + step + 2e-7f * moved_now;   // rounded up generously: the sum must not fall short
+        // Fixed point: this iteration left the pose bit for bit as it was and the solve left its warm-start basis
+        // untouched. The next iteration would then start from the very state this one started from — pose, basis, mu
+        // (the cache never changes a result) — and reproduce it, and so would every iteration up to the next change of
+        // mu (iterations that are multiples of 8, :96-98). They are not run: the loop continues at that iteration, or at
+        // the last one, which is always run so that it leaves its weights and covariance behind. The reference's 128
+        // iterations spend a third of their time in such repeats once the alignment has converged in fp32.
+        int next = iter + 1;
+        bool same = skip_fixed != 0 && !v_moved;
+        for (int k = 0; k < 16; ++k) same = same && Tn[k] == s_T[k];
+        if (same) {
+          const int j = min((iter / 8 + 1) * 8, max_iter - 1);
+          if (j > next) next = j;
+        }
+        s_next = next;
+        s_cum[next & 255] = moved_now + step + 2e-7f * moved_now;   // rounded up generously: the sum must not fall short
       }
       for (int k = 0; k < 16; ++k) s_T[k] = Tn[k];
       if (rank == 0 && P.res && iter == max_iter - 1) for (int k = 0; k < 9; ++k) P.res->cov[k] = cov[k];
@@ -800,7 +820,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
   if (tid == 0) atomicAdd(P.stat, n_searched);
   if (CL) cg::this_cluster().sync();   // nobody leaves while its block sums may still be read
   if (rank != 0) return;
-  if (tid == 0) P.stat[1] = (unsigned long long)P.n * (unsigned long long)max_iter;
+  if (tid == 0) {
+    P.stat[1] = (unsigned long long)P.n * (unsigned long long)max_iter;
+    P.stat[2] = iters_run;
+    P.stat[3] = (unsigned long long)max_iter;
+  }
   if (tid < 16) P.pose[tid] = s_T[tid];  // :156
   if (tid == 0 && P.res) {
     const float mean_cost = sqrtf((float)cost / (float)P.n);  // :157
@@ -816,7 +840,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
 // C * n_pairs <= SM count, at most 16 — beyond 8 is the opt-in cluster size). RST_ICP3D_CLUSTER overrides.
 // Measured on B200, 14 k-point clouds, 128 iterations: one pair 13.4 ms (C = 1) -> 4.6 ms (C = 16) including the
 // depth -> cloud stage; 8 pairs 14.1 -> 5.9 ms (C = 8; C = 16: 7.8 ms).
-cudaError_t launch_icp3d(const PairDesc* descs, int n_pairs, int max_iter, float grid_cell, int forced, float3 cache, cudaStream_t stream) {
+cudaError_t launch_icp3d(const PairDesc* descs, int n_pairs, int max_iter, float grid_cell, int forced, float3 cache, int skip_fixed, cudaStream_t stream) {
   static int sm_counts[64] = {0}, c_maxs[64] = {0};   // per device ordinal (function attributes are per device)
   int dev = 0;
   cudaGetDevice(&dev);
@@ -847,7 +871,7 @@ cudaError_t launch_icp3d(const PairDesc* descs, int n_pairs, int max_iter, float
   if (forced > 0) while (C * 2 <= c_max && C * 2 <= forced) C *= 2;
   else while (C * 2 <= c_max && C * 2 * n_pairs <= (C * 2 > 8 ? sm_count / 2 : sm_count)) C *= 2;   // 16-CTA clusters pack badly: only while they leave half the GPU free
   if (C == 1) {
-    k_icp3d<false><<<n_pairs, kThreads, kRingBytes, stream>>>(descs, max_iter, grid_cell, cache);
+    k_icp3d<false><<<n_pairs, kThreads, kRingBytes, stream>>>(descs, max_iter, grid_cell, cache, skip_fixed);
     return cudaGetLastError();
   }
   cudaLaunchConfig_t cfg{};
@@ -859,7 +883,7 @@ cudaError_t launch_icp3d(const PairDesc* descs, int n_pairs, int max_iter, float
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, k_icp3d<true>, descs, max_iter, grid_cell, cache);
+  return cudaLaunchKernelEx(&cfg, k_icp3d<true>, descs, max_iter, grid_cell, cache, skip_fixed);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1463,7 +1487,8 @@ struct Icp3dState {
   int icp3d_cluster = 0;   // CTAs per pair of k_icp3d, 0 = automatic
   // neighbour cache of k_icp3d: scan margin = clamp(x * motion since the last scan, y * cell, z * cell); z <= 0 = off
   float3 cache = make_float3(kCacheGain, kCacheLo, kCacheHi);
-  unsigned long long searched = 0, queried = 0;   // of the last rst_icp3d_pairs / rst_icp3d_depth call
+  unsigned long long searched = 0, queried = 0, iters_run = 0, iters_asked = 0;   // of the last rst_icp3d_pairs / rst_icp3d_depth call
+  int skip_fixed = 1;   // k_icp3d jumps over iterations that provably repeat the previous one
   // rst_icp3d_depth uploads its frames in chunks on a stream of its own, the depth -> cloud kernels of a chunk waiting
   // for that chunk only
   cudaStream_t copy = nullptr;
@@ -1471,8 +1496,10 @@ struct Icp3dState {
 };
 
 inline void sum_stats(Icp3dState* st, const unsigned long long* s, int n_pairs) {
-  st->searched = st->queried = 0;
-  for (int i = 0; i < n_pairs; ++i) { st->searched += s[2 * i]; st->queried += s[2 * i + 1]; }
+  st->searched = st->queried = st->iters_run = st->iters_asked = 0;
+  for (int i = 0; i < n_pairs; ++i) {
+    st->searched += s[4 * i]; st->queried += s[4 * i + 1]; st->iters_run += s[4 * i + 2]; st->iters_asked += s[4 * i + 3];
+  }
 }
 
 void icp3d_free(void* p) {
@@ -1511,6 +1538,25 @@ extern "C" int32_t rst_set_icp3d_cache(rst_ctx* c, float gain, float lo_cells, f
   void** slot = rst::ctx_ext_slot(c, &free_fn);
   if (!*slot) { *slot = new Icp3dState(); *free_fn = icp3d_free; }
   static_cast<Icp3dState*>(*slot)->cache = make_float3(gain, lo_cells, hi_cells);
+  return RST_OK;
+}
+
+extern "C" int32_t rst_set_icp3d_fixed_point_skip(rst_ctx* c, int32_t on) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  void (**free_fn)(void*) = nullptr;
+  void** slot = rst::ctx_ext_slot(c, &free_fn);
+  if (!*slot) { *slot = new Icp3dState(); *free_fn = icp3d_free; }
+  static_cast<Icp3dState*>(*slot)->skip_fixed = on ? 1 : 0;
+  return RST_OK;
+}
+
+extern "C" int32_t rst_icp3d_iteration_stats(rst_ctx* c, uint64_t* run_out, uint64_t* asked_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  void (**free_fn)(void*) = nullptr;
+  void** slot = rst::ctx_ext_slot(c, &free_fn);
+  const Icp3dState* st = static_cast<const Icp3dState*>(*slot);
+  if (run_out) *run_out = st ? st->iters_run : 0;
+  if (asked_out) *asked_out = st ? st->iters_asked : 0;
   return RST_OK;
 }
 
@@ -1559,7 +1605,7 @@ extern "C" int32_t rst_icp3d_pairs(rst_ctx* c, const rst_cloud* src, const rst_c
   }
   const size_t upload_bytes = off;
   const size_t o_res = off; off = align_up(off + sizeof(rst_icp3d_result) * n_pairs);
-  const size_t o_stat = off; off = align_up(off + sizeof(unsigned long long) * 2 * n_pairs);
+  const size_t o_stat = off; off = align_up(off + sizeof(unsigned long long) * 4 * n_pairs);
   std::vector<size_t> o_nbr(n_pairs), o_w(n_pairs);
   const size_t o_nbr0 = off;
   for (int i = 0; i < n_pairs; ++i) { o_nbr[i] = off; off += sizeof(int) * (size_t)src[i].n; }
@@ -1606,13 +1652,13 @@ extern "C" int32_t rst_icp3d_pairs(rst_ctx* c, const rst_cloud* src, const rst_c
     d.queue = reinterpret_cast<int*>(D + o_queue[i]);
     d.pose = reinterpret_cast<float*>(D + o_pose) + 16 * i;
     d.res = reinterpret_cast<rst_icp3d_result*>(D + o_res) + i;
-    d.stat = reinterpret_cast<unsigned long long*>(D + o_stat) + 2 * i;
+    d.stat = reinterpret_cast<unsigned long long*>(D + o_stat) + 4 * i;
     hd[i] = d;
   }
   std::memcpy(H + o_pose, poses_inout, sizeof(float) * 16 * n_pairs);
   ICP_CUDA(cudaMemcpyAsync(D, H, upload_bytes, cudaMemcpyHostToDevice, stream));
   ICP_CUDA(cudaMemsetAsync(D + o_res, 0, o_nbr0 - o_res, stream));   // results and cache statistics
-  ICP_CUDA(launch_icp3d(reinterpret_cast<const PairDesc*>(D + o_desc), n_pairs, max_iter, grid_cell, st->icp3d_cluster, st->cache, stream));
+  ICP_CUDA(launch_icp3d(reinterpret_cast<const PairDesc*>(D + o_desc), n_pairs, max_iter, grid_cell, st->icp3d_cluster, st->cache, st->skip_fixed, stream));
   rst::ctx_count_launches(c, 1);
   ICP_CUDA(cudaMemcpyAsync(H + o_pose, D + o_pose, sizeof(float) * 16 * n_pairs, cudaMemcpyDeviceToHost, stream));
   const bool want_corr = nbrs_out || weights_out;
@@ -1670,7 +1716,7 @@ extern "C" int32_t rst_icp3d_depth(rst_ctx* c, const rst_frame* frames, int32_t 
   const size_t upload_bytes = off;
   const size_t o_res = off; off = align_up(off + sizeof(rst_icp3d_result) * (size_t)(n_pairs > 0 ? n_pairs : 1));
   const size_t o_cnt = off; off = align_up(off + sizeof(int) * n_frames);
-  const size_t o_stat = off; off = align_up(off + sizeof(unsigned long long) * 2 * (size_t)(n_pairs > 0 ? n_pairs : 1));
+  const size_t o_stat = off; off = align_up(off + sizeof(unsigned long long) * 4 * (size_t)(n_pairs > 0 ? n_pairs : 1));
   const size_t download_end = off;
   const size_t o_depth = off; off = align_up(off + npx * 2 * n_frames);
   const size_t o_cloud = off; off = align_up(off + npx * 12 * n_frames);
@@ -1727,7 +1773,7 @@ extern "C" int32_t rst_icp3d_depth(rst_ctx* c, const rst_frame* frames, int32_t 
     d.queue = reinterpret_cast<int*>(D + o_queue[i]);
     d.pose = reinterpret_cast<float*>(D + o_pose) + 16 * i;
     d.res = reinterpret_cast<rst_icp3d_result*>(D + o_res) + i;
-    d.stat = reinterpret_cast<unsigned long long*>(D + o_stat) + 2 * i;
+    d.stat = reinterpret_cast<unsigned long long*>(D + o_stat) + 4 * i;
     pd[i] = d;
   }
   if (n_pairs > 0) std::memcpy(H + o_pose, poses_inout, sizeof(float) * 16 * n_pairs);
@@ -1747,7 +1793,7 @@ extern "C" int32_t rst_icp3d_depth(rst_ctx* c, const rst_frame* frames, int32_t 
     ICP_CUDA(cudaMemsetAsync(D + o_vals, 0x7f, (size_t)cap * 4 * n_frames, stream));  // 0x7f7f7f7f > any pixel index
   }
   ICP_CUDA(cudaMemsetAsync(D + o_res, 0, sizeof(rst_icp3d_result) * (size_t)(n_pairs > 0 ? n_pairs : 1), stream));
-  ICP_CUDA(cudaMemsetAsync(D + o_stat, 0, sizeof(unsigned long long) * 2 * (size_t)(n_pairs > 0 ? n_pairs : 1), stream));
+  ICP_CUDA(cudaMemsetAsync(D + o_stat, 0, sizeof(unsigned long long) * 4 * (size_t)(n_pairs > 0 ? n_pairs : 1), stream));
   for (int ch = 0; ch < n_chunks; ++ch) {
     const int f0 = (int)((long long)n_frames * ch / n_chunks), f1 = (int)((long long)n_frames * (ch + 1) / n_chunks), nf = f1 - f0;
     cudaStream_t up = n_chunks > 1 ? st->copy : stream;
@@ -1768,7 +1814,7 @@ extern "C" int32_t rst_icp3d_depth(rst_ctx* c, const rst_frame* frames, int32_t 
     rst::ctx_count_launches(c, decimate ? 4 : 3);
   }
   if (n_pairs > 0) {
-    ICP_CUDA(launch_icp3d(reinterpret_cast<const PairDesc*>(D + o_pdesc), n_pairs, max_iter, grid_cell, st->icp3d_cluster, st->cache, stream));
+    ICP_CUDA(launch_icp3d(reinterpret_cast<const PairDesc*>(D + o_pdesc), n_pairs, max_iter, grid_cell, st->icp3d_cluster, st->cache, st->skip_fixed, stream));
     rst::ctx_count_launches(c, 1);
     ICP_CUDA(cudaMemcpyAsync(H + o_pose, D + o_pose, sizeof(float) * 16 * n_pairs, cudaMemcpyDeviceToHost, stream));
   }

@@ -33,6 +33,15 @@ for cell in (0.1,):
             t0 = time.perf_counter(); al.icp3d_depth(frames[:2], s[:1], d[:1], intr, max_iter=128, grid_cell=cell); one = min(one, time.perf_counter() - t0)
         print(f"cell {cell} cache {st}: 128 pairs {best*1e3:8.2f} ms = {128/best:8.0f} pairs/s, single pair {one*1e3:6.2f} ms, bit-identical to cache off: {same}, searched {sq[0] / max(sq[1], 1):.4f} of {sq[1]} queries", flush=True)
 al.set_icp3d_cache()
+for on in (False, True):
+    al.set_icp3d_fixed_point_skip(on)
+    best, one = 1e9, 1e9
+    for _ in range(3):
+        t0 = time.perf_counter(); ok, T, mc, cnt = al.icp3d_depth(frames, s, d, intr, max_iter=128); best = min(best, time.perf_counter() - t0)
+    it_stats = al.icp3d_iteration_stats()
+    for _ in range(5):
+        t0 = time.perf_counter(); al.icp3d_depth(frames[:2], s[:1], d[:1], intr, max_iter=128); one = min(one, time.perf_counter() - t0)
+    print(f"fixed-point skip {on}: 128 pairs {best*1e3:8.2f} ms = {128/best:8.0f} pairs/s, single pair {one*1e3:6.2f} ms, iterations run {it_stats}, bit-identical: {np.array_equal(T, base)}", flush=True)
 for it in (0, 1, 2, 4, 8, 16, 32, 64, 128):
     best = 1e9
     for _ in range(3):

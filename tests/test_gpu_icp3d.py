@@ -256,7 +256,8 @@ def test_neighbour_cache_ties_long_runs_and_large_motion(al):
                 al.set_icp3d_cache(0.0, 0.0, 0.0)
                 ok0, Ta, ex0 = al.icp3d_pairs([s_], [d_], it, T0=T0, details=True)
                 searched0, queried0 = al.icp3d_cache_stats()
-                assert queried0 == len(s_) * it and searched0 == queried0
+                run0, asked0 = al.icp3d_iteration_stats()
+                assert queried0 == len(s_) * it and asked0 == it and searched0 == len(s_) * run0   # cache off: every iteration that ran searched every point
                 al.set_icp3d_cache()
                 ok1, Tb, ex1 = al.icp3d_pairs([s_], [d_], it, T0=T0, details=True)
                 searched1, queried1 = al.icp3d_cache_stats()
@@ -271,3 +272,38 @@ def test_neighbour_cache_ties_long_runs_and_large_motion(al):
     finally:
         al.set_icp3d_cluster(0)
         al.set_icp3d_cache()
+
+
+def test_fixed_point_skip_changes_nothing_but_time(al):
+    """rst_set_icp3d_fixed_point_skip: once an iteration returns the pose it was given bit for bit (and its SVD warm-start
+    basis unchanged), the iterations up to the next change of mu would repeat it exactly and are not run. Same
+    neighbours, weights, covariance, cost, mu and pose as running every iteration — for odd iteration counts, counts
+    that end inside a skipped stretch, one CTA per pair and clusters, cache on and off; and iterations are saved."""
+    src, dst = depth_clouds(1, 0)
+    src2, dst2 = GOLD["src"], GOLD["dst"]
+    T0 = synth.make_pose(synth.rotvec_to_R([0.01, -0.02, 0.01]), [0.02, 0.01, -0.03])
+    saved = 0
+    try:
+        for cl in (1, 4):
+            al.set_icp3d_cluster(cl)
+            for cache in ((1.0, 0.05, 0.2), (0.0, 0.0, 0.0)):
+                al.set_icp3d_cache(*cache)
+                for it in (128, 61, 30, 23, 9):
+                    al.set_icp3d_fixed_point_skip(False)
+                    ok0, Ta, ex0 = al.icp3d_pairs([src, src2], [dst, dst2], it, T0=T0, details=True)
+                    assert al.icp3d_iteration_stats() == (2 * it, 2 * it)
+                    al.set_icp3d_fixed_point_skip(True)
+                    ok1, Tb, ex1 = al.icp3d_pairs([src, src2], [dst, dst2], it, T0=T0, details=True)
+                    run, asked = al.icp3d_iteration_stats()
+                    assert asked == 2 * it and 2 <= run <= asked
+                    saved += asked - run
+                    assert np.array_equal(Ta, Tb) and np.array_equal(ok0, ok1), (cl, cache, it)
+                    for i in range(2):
+                        assert np.array_equal(ex0[i]["nbrs"], ex1[i]["nbrs"]) and np.array_equal(ex0[i]["weights"], ex1[i]["weights"])
+                        assert np.array_equal(ex0[i]["cov"], ex1[i]["cov"]) and ex0[i]["mean_cost"] == ex1[i]["mean_cost"]
+                        assert ex0[i]["mu"] == ex1[i]["mu"]
+        assert saved > 0, "no iteration was ever skipped on converging pairs"
+    finally:
+        al.set_icp3d_cluster(0)
+        al.set_icp3d_cache()
+        al.set_icp3d_fixed_point_skip(True)
