@@ -602,15 +602,20 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             dtr = (time.perf_counter() - t0r) / reps
             rerr = np.array([synth.pose_error(Tr[i], gt[i]) for i in range(n_pairs)])
             searched, queried = al.icp3d_cache_stats()
-            al.set_icp3d_cache(0.0, 0.0, 0.0)                              # every point searches in every iteration
+            it_run, it_asked = al.icp3d_iteration_stats()
+            al.set_icp3d_cache(0.0, 0.0, 0.0)                              # every point searches in every iteration ...
+            al.set_icp3d_fixed_point_skip(False)                           # ... and every iteration runs: the reference's schedule as written
             t0n = time.perf_counter()
             okn, Tn_, _, _ = al.icp3d_depth(frames, sidx, didx, intr)
             dt_nocache = time.perf_counter() - t0n
             al.set_icp3d_cache()
+            al.set_icp3d_fixed_point_skip(True)
             cache = {"searched": searched, "queried": queried, "searched_fraction": searched / max(queried, 1),
-                     "without_cache_pairs_per_s": n_pairs / dt_nocache, "poses_bit_identical_to_without_cache": bool(np.array_equal(Tn_, Tr)),
+                     "iterations_run": it_run, "iterations_asked": it_asked,
+                     "without_cache_and_skip_pairs_per_s": n_pairs / dt_nocache, "poses_bit_identical_to_without": bool(np.array_equal(Tn_, Tr)),
                      "what": "a query searches only when |p' - nbr| + (motion since the entry was proven) >= the proven radius (triangle inequality); "
-                             "indices and distances are those of a search, bit for bit"}
+                             "an iteration is not run when the previous one returned its pose bit for bit (it would repeat it until mu changes); "
+                             "indices, distances and poses are those of searching every point in every iteration, bit for bit"}
             # one pair at a time, as the reference's caller runs it (rs_replay_app.cpp:246-251): one CTA per pair vs the
             # automatic thread-block cluster per pair
             single = {}
