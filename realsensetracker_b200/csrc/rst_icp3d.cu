@@ -601,8 +601,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_icp3d(const PairDesc* __restric
   if (tid == 0) s_qn = 0;
   // per source point, two 16-byte records so that no pass of an iteration gathers or chases an index:
   //   sl[i] = (source point, L | k): the proven radius of the neighbour cache with, in its 8 lowest mantissa bits,
-  //           the iteration (mod 256) whose pose the point had when L was proven — that position is recomputed
-  //           from the pose history in shared memory instead of being stored;
+  //           the iteration (mod 256) whose pose the point had when L was proven — how far it has moved since is
+  //           bounded by the path length s_cum[now] - s_cum[k] instead of storing that position;
   //   qd[i] = (coordinates of the current neighbour, squared distance to it).
   for (int i = first; i < P.n; i += stride) {
     P.sl[i] = make_float4(P.src[3 * i], P.src[3 * i + 1], P.src[3 * i + 2], 0.f);   // L = 0: nothing proven yet
