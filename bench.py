@@ -595,11 +595,18 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         if world == 1 and not args.no_cpu:
             sidx, didx = np.arange(1, FRAMES, dtype=np.int32), np.arange(0, FRAMES - 1, dtype=np.int32)
             al.icp3d_depth(frames, sidx, didx, intr)                       # warm-up (allocations)
+            # wall clock of the blocking call AND, beside it, CUDA events on the context's stream around the same calls
+            # (that stream waits for the chunked uploads, so the span covers H2D + depth -> cloud + ICP + D2H)
+            evr0, evr1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0r = time.perf_counter()
             reps = 3
+            evr0.record(stream)
             for _ in range(reps):
                 okr, Tr, mcr, cnts = al.icp3d_depth(frames, sidx, didx, intr)
+            evr1.record(stream)
+            evr1.synchronize()
             dtr = (time.perf_counter() - t0r) / reps
+            dev_ms_batch = evr0.elapsed_time(evr1) / reps
             rerr = np.array([synth.pose_error(Tr[i], gt[i]) for i in range(n_pairs)])
             searched, queried = al.icp3d_cache_stats()
             it_run, it_asked = al.icp3d_iteration_stats()
@@ -623,9 +630,13 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                 al.set_icp3d_cluster(ctas)
                 al.icp3d_depth(frames[:2], sidx[:1], didx[:1], intr)
                 t0s = time.perf_counter()
+                evr0.record(stream)
                 for _ in range(10):
                     al.icp3d_depth(frames[:2], sidx[:1], didx[:1], intr)
+                evr1.record(stream)
+                evr1.synchronize()
                 single[name + "_ms"] = (time.perf_counter() - t0s) / 10 * 1e3
+                single[name + "_cuda_events_ms"] = evr0.elapsed_time(evr1) / 10
             al.set_icp3d_cluster(0)
             # the cloud utilities and the GICP alignment of the reference's align library on one pair's clouds
             # (host clouds in, results out, best of 5 blocking calls each)
@@ -647,6 +658,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             Tg_, _ = al.gicp_align(src_c, dst_c)
             utils["gicp_pose_err_vs_gt_t_m"] = float(synth.pose_error(Tg_, gt[0])[0])
             ref_gpu = {"value": n_pairs / dtr, "single_pair": single, "unit": "pairs/s", "ms_per_step": dtr * 1e3, "timing": "host wall clock, H2D + D2H included",
+                       "cuda_events_ms_per_step": dev_ms_batch, "cuda_events_pairs_per_s": n_pairs / (dev_ms_batch * 1e-3),
                        "algorithm": "reference AlignIcp3d on the GPU: exact grid NN, GM/GNC weights, Kabsch, 128 iterations, voxel 0.05",
                        "mean_cloud_points": float(np.mean(cnts)), "pairs_ok": int(okr.sum()), "neighbour_cache": cache, "cloud_utilities": utils,
                        "pose_err_vs_gt": {"t_m_max": float(rerr[:, 0].max()), "r_rad_max": float(rerr[:, 1].max())}}
