@@ -156,7 +156,10 @@ __device__ Grid build_grid(const float* __restrict__ pts, int n, float grid_cell
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int j = tid; j < n; j += kThreads)
-    for (int a = 0; a < 3; ++a) { const float v = pts[3 * j + a]; lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+    for (int a = 0; a < 3; ++a) {   // the box of the FINITE coordinates: an infinite one would make the cell counts overflow
+      const float v = pts[3 * j + a];
+      if (fabsf(v) <= FLT_MAX) { lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+    }
   for (int a = 0; a < 3; ++a)
     for (int o = 16; o > 0; o >>= 1) {
       lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
@@ -169,14 +172,16 @@ __device__ Grid build_grid(const float* __restrict__ pts, int n, float grid_cell
     for (int a = 0; a < 3; ++a) {
       bl[a] = FLT_MAX; bh[a] = -FLT_MAX;
       for (int w = 0; w < kWarps; ++w) { bl[a] = fminf(bl[a], s_lohi[w][a]); bh[a] = fmaxf(bh[a], s_lohi[w][3 + a]); }
+      if (!(bh[a] >= bl[a])) { bl[a] = 0.f; bh[a] = 0.f; }   // no finite coordinate on this axis: one cell
     }
     Grid g;
     g.lox = bl[0]; g.loy = bl[1]; g.loz = bl[2];
     const float ex = bh[0] - bl[0], ey = bh[1] - bl[1], ez = bh[2] - bl[2];
     float h = grid_cell > 0.f ? grid_cell : fmaxf(fmaxf(ex, fmaxf(ey, ez)) / 64.f, 1e-6f);
     for (;;) {
-      g.nx = (int)floorf(ex / h) + 1; g.ny = (int)floorf(ey / h) + 1; g.nz = (int)floorf(ez / h) + 1;
-      if ((long long)g.nx * g.ny * g.nz <= kCellCap) break;
+      // counted in floating point first: a tiny grid_cell must not overflow the int conversion
+      const float fx = floorf(ex / h) + 1.f, fy = floorf(ey / h) + 1.f, fz = floorf(ez / h) + 1.f;
+      if ((double)fx * (double)fy * (double)fz <= (double)kCellCap) { g.nx = (int)fx; g.ny = (int)fy; g.nz = (int)fz; break; }
       h *= 1.26f;
     }
     g.h = h; g.inv_h = 1.0f / h;

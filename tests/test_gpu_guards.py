@@ -41,6 +41,37 @@ def test_cloud_icp_survives_non_finite_points_and_poses():
         al.close()
 
 
+def test_gridded_cloud_with_infinite_points_or_a_tiny_cell():
+    """The uniform grid is laid over the FINITE coordinates of the gridded (target) cloud and its cell count is
+    bounded before the conversion to int: an infinite point or a grid_cell far below the cloud's resolution must
+    neither overflow the grid dimensions nor change anybody's nearest neighbour (an infinite point is at infinite
+    distance from every query)."""
+    src, dst = GOLD["src"], GOLD["dst"]
+    far = np.array([[np.inf, 0.0, 0.0], [0.0, -np.inf, 0.0]], np.float32)
+    dst_bad = np.vstack([dst, far])                           # appended: the indices of the finite points are unchanged
+    al = Aligner(16, 16, 2, 1)
+    try:
+        idx0, d20 = al.find_correspondences(dst, src)
+        idx1, d21 = al.find_correspondences(dst_bad, src)
+        assert np.array_equal(idx0, idx1) and np.array_equal(d20, d21)
+        idx2, d22 = al.find_correspondences(dst, src, grid_cell=1e-12)     # the cell is grown until the grid fits
+        assert np.array_equal(idx0, idx2) and np.array_equal(d20, d22)
+        idx3, d23 = al.find_correspondences(np.full((4, 3), np.inf, np.float32), src)   # no finite point at all: one cell
+        assert ((idx3 >= 0) & (idx3 < 4)).all()
+        n0 = al.cloud_normals(dst, 16)
+        n1 = al.cloud_normals(dst_bad, 16)
+        assert np.allclose(n0, n1[:len(dst)], atol=1e-6)
+        c1 = al.cloud_covariances(dst_bad)
+        assert np.isfinite(c1[:len(dst)]).all()
+        ok0, T0 = al.icp3d_pairs([src], [dst], 32)
+        ok1, T1 = al.icp3d_pairs([src], [dst_bad], 32)
+        assert ok0[0] and ok1[0]
+        dt, dr = synth.pose_error(T1[0], T0[0])
+        assert dt < 1e-5 and dr < 1e-5
+    finally:
+        al.close()
+
+
 def test_device_bound_frames_reject_slots_outside_the_bound_range(seq_small):
     import torch
     frames, gt, intr = seq_small
