@@ -18,6 +18,7 @@
 #include <array>
 #include <cstdint>
 #include <cstring>
+#include <limits>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -222,6 +223,40 @@ inline void FindCorrespondences(AlignContext& ctx, const Cloud& target, const Cl
   if (s.n) rst_find_correspondences(ctx.get(), &t, &s, /*grid_cell=*/0.f, indices->data(), squared_distances->data());
 }
 
+/// void ComputeCentroid(cloud, &centroid)  point_cloud_utils.cpp:92-98; centroid_xyz: 3 floats.
+template <class Cloud>
+inline void ComputeCentroid(AlignContext& ctx, const Cloud& cloud, float* const centroid_xyz) {
+  const rst_cloud c{cloud.GetPtr(), static_cast<std::int32_t>(cloud.GetNumPoints())};
+  if (rst_cloud_centroid(ctx.get(), &c, centroid_xyz) != RST_OK)
+    centroid_xyz[0] = centroid_xyz[1] = centroid_xyz[2] = std::numeric_limits<float>::quiet_NaN();   // 0 / 0 in the reference
+}
+
+/// void ComputeCovariances(tree, cloud, &covs, use_gicp)  point_cloud_utils.cpp:100-161; covs_9n: n x 9 floats
+/// (symmetric 3x3 each, so row- and column-major agree).
+template <class Cloud>
+inline void ComputeCovariances(AlignContext& ctx, const Cloud& cloud, float* const covs_9n, const bool use_gicp) {
+  const rst_cloud c{cloud.GetPtr(), static_cast<std::int32_t>(cloud.GetNumPoints())};
+  rst_cloud_covariances(ctx.get(), &c, use_gicp ? 1 : 0, /*grid_cell=*/0.f, covs_9n);
+}
+
+/// void ComputeNormals(cloud, tree, num_neighbors, &normals)  point_cloud_utils.cpp:176-203. The reference leaves the
+/// sign of each normal to its eigen-solver; here every normal comes back pointing towards the origin (one of those
+/// signs), and OrientNormals re-orients it for any other viewpoint.
+template <class Cloud>
+inline void ComputeNormals(AlignContext& ctx, const Cloud& cloud, const float num_neighbors, Cloud* const normals) {
+  const rst_cloud c{cloud.GetPtr(), static_cast<std::int32_t>(cloud.GetNumPoints())};
+  const float origin[3] = {0.f, 0.f, 0.f};
+  normals->SetNumPoints(c.n);
+  if (c.n) rst_cloud_normals(ctx.get(), &c, static_cast<std::int32_t>(num_neighbors), origin, /*grid_cell=*/0.f, normals->GetPtr());
+}
+
+/// void OrientNormals(cloud, viewpoint, &normals)  point_cloud_utils.cpp:205-216; viewpoint_xyz: 3 floats.
+template <class Cloud>
+inline void OrientNormals(AlignContext& ctx, const Cloud& cloud, const float* const viewpoint_xyz, Cloud* const normals) {
+  const rst_cloud c{cloud.GetPtr(), static_cast<std::int32_t>(cloud.GetNumPoints())};
+  if (c.n && normals->GetNumPoints() == cloud.GetNumPoints()) rst_orient_normals(ctx.get(), &c, viewpoint_xyz, normals->GetPtr());
+}
+
 /// The process-wide context the literal (context-free) signatures below run on: created on first use on CUDA device
 /// RS_TRACKER_ALIGN_DEVICE (default 0). The cloud engine sizes its own device memory per call, so the frame capacity
 /// of this context is minimal; use an explicit AlignContext for the frame-based calls.
@@ -283,6 +318,33 @@ template <class Tree, class Cloud>
 inline auto FindCorrespondences(const Tree& tree, const Cloud& source, std::vector<int>* const indices,
                                 std::vector<float>* const squared_distances) -> decltype(tree.m_cloud.get(), void()) {
   FindCorrespondences(DefaultAlignContext(), tree.m_cloud.get(), source, indices, squared_distances);
+}
+
+/// void ComputeCentroid(const Cloud3f& cloud, Eigen::Vector3f* const centroid)  (align_icp.cpp:86 calls it)
+template <class Cloud>
+inline void ComputeCentroid(const Cloud& cloud, Eigen::Vector3f* const centroid) {
+  ComputeCentroid(DefaultAlignContext(), cloud, centroid->data());
+}
+/// void ComputeCovariances(const KDTree3f& tree, const Cloud3f& cloud, std::vector<Eigen::Matrix3f>* const covs,
+/// const bool use_gicp)  (align_gicp.cpp:121,123); the tree is accepted and not used (the GPU grids the cloud itself).
+template <class Tree, class Cloud>
+inline void ComputeCovariances(const Tree& /*tree*/, const Cloud& cloud, std::vector<Eigen::Matrix3f>* const covs, const bool use_gicp) {
+  const std::size_t n = static_cast<std::size_t>(cloud.GetNumPoints());
+  std::vector<float> flat(9 * n);
+  if (n) ComputeCovariances(DefaultAlignContext(), cloud, flat.data(), use_gicp);
+  covs->resize(n);
+  for (std::size_t i = 0; i < n; ++i) std::memcpy((*covs)[i].data(), flat.data() + 9 * i, sizeof(float) * 9);
+}
+/// void ComputeNormals(const Cloud3f& cloud, const KDTree3f& tree, const float num_neighbors, Cloud3f* const normals)
+/// (rs_replay_app.cpp:386)
+template <class Cloud, class Tree>
+inline void ComputeNormals(const Cloud& cloud, const Tree& /*tree*/, const float num_neighbors, Cloud* const normals) {
+  ComputeNormals(DefaultAlignContext(), cloud, num_neighbors, normals);
+}
+/// void OrientNormals(const Cloud3f& cloud, const Vector3f& viewpoint, Cloud3f* const normals)  (rs_replay_app.cpp:387)
+template <class Cloud>
+inline void OrientNormals(const Cloud& cloud, const Eigen::Vector3f& viewpoint, Cloud* const normals) {
+  OrientNormals(DefaultAlignContext(), cloud, viewpoint.data(), normals);
 }
 
 /// Drop-in signature for the reference's call sites (rs_replay_app.cpp:251, rs_align_app.cpp:303).

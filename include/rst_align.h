@@ -410,6 +410,14 @@ int32_t rst_downsample_voxel(rst_ctx* ctx, const rst_cloud* cloud_in, float voxe
 /* RemoveNans(cloud_in, &cloud_out)  point_cloud_utils.cpp:163-174: keeps the points whose three coordinates are finite,
  *   in order. xyz_out must hold cloud_in->n points. */
 int32_t rst_remove_nans(rst_ctx* ctx, const rst_cloud* cloud_in, float* xyz_out, int32_t* n_out);
+/* ComputeCentroid(cloud, &centroid)  point_cloud_utils.cpp:92-98: mean of the points, summed in fp64 in a fixed order
+ *   (the reference sums sequentially in fp32: equal to fp32 round-off of that sum). centroid_out: 3 floats. An empty
+ *   cloud is RST_ERR_INVALID_ARG (the reference divides by zero). */
+int32_t rst_cloud_centroid(rst_ctx* ctx, const rst_cloud* cloud, float* centroid_out);
+/* OrientNormals(cloud, viewpoint, &normals)  point_cloud_utils.cpp:205-216: normals_inout[i] is negated where
+ *   (cloud[i] - viewpoint) . normals_inout[i] > 0. rst_cloud_normals() already orients its output; this is for normals
+ *   that come from elsewhere or for a second viewpoint. viewpoint: 3 floats; normals_inout: n x 3 floats. */
+int32_t rst_orient_normals(rst_ctx* ctx, const rst_cloud* cloud, const float* viewpoint, float* normals_inout);
 
 /* GICP plane-to-plane (rs_tracker/align: gicp_cost.hpp:40-73, align_gicp.cpp:41-163) on the device.
  * Residual of correspondence i -> j = dst_indices[i]:  e = C^{-1/2} (R s_i + t - d_j),  C = C_d[j] + R C_s[i] R^T,

@@ -414,6 +414,16 @@ def ref_normals(pts, k=16, viewpoint=(0.0, 0.0, 0.0)):
     return out
 
 
+def ref_orient_normals(pts, viewpoint, normals):
+    """OrientNormals (point_cloud_utils.cpp:205-216) through the compiled reference: a flipped copy of `normals`."""
+    p = _f32(pts)
+    vp = _f32(viewpoint)
+    out = np.array(normals, dtype=np.float32, order="C", copy=True)
+    ref_lib().ref_orient_normals(p.ctypes.data_as(C.c_void_p), C.c_int32(len(p)), vp.ctypes.data_as(C.c_void_p),
+                                 out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def ref_align_depth_pairs(src, dst, intr, depth_scale=0.001, voxel=0.05, max_iter=128, n_threads=1):
     """Batch of depth pairs through the reference's own RemoveNans / DownsampleVoxel / AlignIcp3d."""
     n, h, w = src.shape

@@ -107,4 +107,11 @@ void ref_normals(const float* pts, int n, int k, const float* viewpoint, float* 
   rs_tracker::OrientNormals(s, Eigen::Vector3f(viewpoint[0], viewpoint[1], viewpoint[2]), &nrm);
   std::memcpy(out, nrm.GetPtr(), sizeof(float) * 3 * n);
 }
+
+// OrientNormals alone (point_cloud_utils.cpp:205-216) on caller-supplied normals, in place
+void ref_orient_normals(const float* pts, int n, const float* viewpoint, float* normals_inout) {
+  Cloud3f s, nrm; to_cloud(pts, n, &s); to_cloud(normals_inout, n, &nrm);
+  rs_tracker::OrientNormals(s, Eigen::Vector3f(viewpoint[0], viewpoint[1], viewpoint[2]), &nrm);
+  std::memcpy(normals_inout, nrm.GetPtr(), sizeof(float) * 3 * n);
+}
 }

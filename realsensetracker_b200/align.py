@@ -190,6 +190,25 @@ class Aligner:
         self._check(self._lib.rst_find_correspondences(self._ctx, C.byref(ct), C.byref(cs), grid_cell, idx.ctypes.data, d2.ctypes.data))
         return idx, d2
 
+    def cloud_centroid(self, cloud) -> np.ndarray:
+        """ComputeCentroid(cloud, &centroid) (point_cloud_utils.cpp:92-98) on the GPU: [3] float32."""
+        S = np.ascontiguousarray(cloud, dtype=np.float32)
+        out = np.empty(3, dtype=np.float32)
+        cs = N.Cloud(S.ctypes.data, len(S))
+        self._check(self._lib.rst_cloud_centroid(self._ctx, C.byref(cs), out.ctypes.data))
+        return out
+
+    def orient_normals(self, cloud, viewpoint, normals) -> np.ndarray:
+        """OrientNormals(cloud, viewpoint, &normals) (point_cloud_utils.cpp:205-216) on the GPU: a flipped copy of `normals`."""
+        S = np.ascontiguousarray(cloud, dtype=np.float32)
+        vp = np.ascontiguousarray(viewpoint, dtype=np.float32)
+        out = np.array(normals, dtype=np.float32, order="C", copy=True)
+        if out.shape != S.shape:
+            raise ValueError("normals must have the cloud's shape")
+        cs = N.Cloud(S.ctypes.data, len(S))
+        self._check(self._lib.rst_orient_normals(self._ctx, C.byref(cs), vp.ctypes.data, out.ctypes.data))
+        return out
+
     def cloud_covariances(self, cloud, use_gicp: bool = False, grid_cell: float = 0.0) -> np.ndarray:
         """ComputeCovariances(tree, cloud, &covs, use_gicp) (point_cloud_utils.cpp:100-161) on the GPU: [n,3,3] float32."""
         S = np.ascontiguousarray(cloud, dtype=np.float32)

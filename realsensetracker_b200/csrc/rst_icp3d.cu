@@ -1269,6 +1269,37 @@ __global__ void __launch_bounds__(128) k_covariances(const Grid* __restrict__ gp
   for (int e = 0; e < 9; ++e) covs[9 * (size_t)i + e] = C[e];
 }
 
+// ComputeCentroid (point_cloud_utils.cpp:92-98) for a caller that holds a cloud: one block, fp64 partial sums in a
+// fixed order (thread-strided, warp butterfly, warps in order), so the result is deterministic; the reference sums
+// sequentially in fp32, this sum is the more accurate one (they agree to fp32 round-off of the n-term sum).
+__global__ void __launch_bounds__(kThreads, 1) k_centroid(const float* __restrict__ pts, int n, float* __restrict__ out) {
+  __shared__ double s_part[kWarps][3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int j = tid; j < n; j += kThreads)
+    for (int a = 0; a < 3; ++a) acc[a] += (double)pts[3 * j + a];
+  for (int a = 0; a < 3; ++a)
+    for (int o = 16; o > 0; o >>= 1) acc[a] += __shfl_xor_sync(0xffffffffu, acc[a], o);
+  if (lane == 0) for (int a = 0; a < 3; ++a) s_part[warp][a] = acc[a];
+  __syncthreads();
+  if (tid < 3) {
+    double t = 0.0;
+    for (int w = 0; w < kWarps; ++w) t += s_part[w][tid];
+    out[tid] = (float)(t * (1.0 / (double)n));
+  }
+}
+
+// OrientNormals (point_cloud_utils.cpp:205-216): a normal that points along the viewing ray p - viewpoint is negated.
+__global__ void __launch_bounds__(256) k_orient_normals(const float* __restrict__ pts, int n, float vx, float vy, float vz,
+                                                        float* __restrict__ normals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float rx = subrn(pts[3 * i], vx), ry = subrn(pts[3 * i + 1], vy), rz = subrn(pts[3 * i + 2], vz);
+  const float nx = normals[3 * i], ny = normals[3 * i + 1], nz = normals[3 * i + 2];
+  const float dot = addrn(mulrn(rx, nx), addrn(mulrn(ry, ny), mulrn(rz, nz)));
+  if (dot > 0.f) { normals[3 * i] = -nx; normals[3 * i + 1] = -ny; normals[3 * i + 2] = -nz; }
+}
+
 // DownsampleVoxel (point_cloud_utils.cpp:34-68) for a cloud: key = floor(p / voxel), the FIRST point of a voxel wins.
 // Pass 1 (any number of blocks): atomicMin(point index) per voxel in an open-addressing table.
 __global__ void __launch_bounds__(256) k_voxel_insert(const float* __restrict__ pts, int n, float voxel, unsigned long long* keys,
@@ -2105,6 +2136,54 @@ extern "C" int32_t rst_cloud_covariances(rst_ctx* c, const rst_cloud* cloud, int
   CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.H + o_cov, k.D + o_cov, 36 * n, cudaMemcpyDeviceToHost, k.stream), "D2H"));
   CLOUD_TRY(k.cuda(cudaStreamSynchronize(k.stream), "sync"));
   std::memcpy(covs_out, k.H + o_cov, 36 * n);
+  return RST_OK;
+}
+
+/* void ComputeCentroid(cloud, &centroid)  point_cloud_utils.cpp:92-98 */
+extern "C" int32_t rst_cloud_centroid(rst_ctx* c, const rst_cloud* cloud, float* centroid_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  CloudCall k(c);
+  if (!cloud_ok(cloud) || !centroid_out) return k.fail(RST_ERR_INVALID_ARG, "null argument / bad cloud");
+  if (cloud->n == 0) return k.fail(RST_ERR_INVALID_ARG, "the cloud is empty");   // the reference divides by zero here
+  CLOUD_TRY(k.begin());
+  const size_t n = (size_t)cloud->n;
+  const size_t o_pts = k.take(12 * n);
+  const size_t upload = k.off;
+  const size_t o_cen = k.take(12);
+  const size_t host_end = k.off;
+  CLOUD_TRY(k.commit(host_end));
+  std::memcpy(k.H + o_pts, cloud->xyz, 12 * n);
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.D, k.H, upload, cudaMemcpyHostToDevice, k.stream), "H2D"));
+  k_centroid<<<1, kThreads, 0, k.stream>>>(reinterpret_cast<const float*>(k.D + o_pts), (int)n, reinterpret_cast<float*>(k.D + o_cen));
+  CLOUD_TRY(k.cuda(cudaGetLastError(), "launch"));
+  rst::ctx_count_launches(c, 1);
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.H + o_cen, k.D + o_cen, 12, cudaMemcpyDeviceToHost, k.stream), "D2H"));
+  CLOUD_TRY(k.cuda(cudaStreamSynchronize(k.stream), "sync"));
+  std::memcpy(centroid_out, k.H + o_cen, 12);
+  return RST_OK;
+}
+
+/* void OrientNormals(cloud, viewpoint, &normals)  point_cloud_utils.cpp:205-216 */
+extern "C" int32_t rst_orient_normals(rst_ctx* c, const rst_cloud* cloud, const float* viewpoint, float* normals_inout) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  CloudCall k(c);
+  if (!cloud_ok(cloud) || !viewpoint || !normals_inout) return k.fail(RST_ERR_INVALID_ARG, "null argument / bad cloud");
+  if (cloud->n == 0) return RST_OK;
+  CLOUD_TRY(k.begin());
+  const size_t n = (size_t)cloud->n;
+  const size_t o_pts = k.take(12 * n), o_nrm = k.take(12 * n);
+  const size_t host_end = k.off;
+  CLOUD_TRY(k.commit(host_end));
+  std::memcpy(k.H + o_pts, cloud->xyz, 12 * n);
+  std::memcpy(k.H + o_nrm, normals_inout, 12 * n);
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.D, k.H, host_end, cudaMemcpyHostToDevice, k.stream), "H2D"));
+  k_orient_normals<<<(unsigned)((n + 255) / 256), 256, 0, k.stream>>>(reinterpret_cast<const float*>(k.D + o_pts), (int)n, viewpoint[0],
+                                                                      viewpoint[1], viewpoint[2], reinterpret_cast<float*>(k.D + o_nrm));
+  CLOUD_TRY(k.cuda(cudaGetLastError(), "launch"));
+  rst::ctx_count_launches(c, 1);
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.H + o_nrm, k.D + o_nrm, 12 * n, cudaMemcpyDeviceToHost, k.stream), "D2H"));
+  CLOUD_TRY(k.cuda(cudaStreamSynchronize(k.stream), "sync"));
+  std::memcpy(normals_inout, k.H + o_nrm, 12 * n);
   return RST_OK;
 }
 

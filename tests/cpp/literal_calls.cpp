@@ -7,8 +7,13 @@
 //   rs_align_app.cpp:303        AlignIcp3d(src_cloud, dst_cloud, 128, &xfm)
 //   align_icp.cpp:165-166       AlignIcp3d(src, dst, dst_tree, max_iter, transform)
 //   point_cloud_utils.hpp:14    FindCorrespondences(tree, source, &indices, &squared_distances)
+//   rs_replay_app.cpp:382-387   KDTree3f tree{std::cref(cloud_transformed), 16}; ComputeNormals(cloud_transformed, tree, 16, &normals);
+//                               OrientNormals(cloud_transformed, viewpoint, &normals)
+//   align_gicp.cpp:120-121      std::vector<Eigen::Matrix3f> src_covs(src.GetNumPoints()); ComputeCovariances(*src_tree, src, &src_covs, false)
+//   point_cloud_utils.hpp:16    ComputeCentroid(cloud, &centroid)   (align_icp.cpp:86)
 #include <cmath>
 #include <cstdio>
+#include <memory>
 #include <random>
 
 #include "rs_tracker/common/types.hpp"       // the reference's own header: Cloud3f, KDTree3f
@@ -105,6 +110,46 @@ int main() {
     with_nan.GetPtr()[3 * 5 + 1] = std::nanf("");
     rs_tracker::RemoveNans(with_nan, &clean);
     if (clean.GetNumPoints() != n - 1) { std::printf("RemoveNans kept %d\n", clean.GetNumPoints()); ++failures; }
+  }
+  // rs_replay_app.cpp:382-387, align_gicp.cpp:114-121, align_icp.cpp:86
+  {
+    const rs_tracker::Cloud3f& cloud_transformed = dst_cloud;
+    const Eigen::Vector3f viewpoint(0.f, 0.f, 5.f);
+    rs_tracker::KDTree3f tree{std::cref(cloud_transformed), 16};
+    rs_tracker::Cloud3f normals;
+    rs_tracker::ComputeNormals(cloud_transformed, tree, 16, &normals);
+    rs_tracker::OrientNormals(cloud_transformed, viewpoint, &normals);
+    int bad = normals.GetNumPoints() != n;
+    for (int i = 0; i < n && !bad; ++i) {
+      const float* nv = normals.GetPtr() + 3 * i;
+      const float len = std::sqrt(nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2]);
+      const float ray = (d[3 * i] - 0.f) * nv[0] + (d[3 * i + 1] - 0.f) * nv[1] + (d[3 * i + 2] - 5.f) * nv[2];
+      if (!(std::fabs(len - 1.f) < 1e-3f) || ray > 1e-6f) ++bad;
+    }
+    std::printf("ComputeNormals + OrientNormals: %d normals, %d not unit / not facing the viewpoint\n", normals.GetNumPoints(), bad);
+    if (bad) ++failures;
+
+    const rs_tracker::Cloud3f& src = src_cloud;
+    std::shared_ptr<rs_tracker::KDTree3f> src_tree = std::make_shared<rs_tracker::KDTree3f>(std::cref(src), 10);
+    std::vector<Eigen::Matrix3f> src_covs(src.GetNumPoints());
+    rs_tracker::ComputeCovariances(*src_tree, src, &src_covs, false);
+    int bad_cov = (int)src_covs.size() != n;
+    for (int i = 0; i < n && !bad_cov; i += 53) {
+      const Eigen::Matrix3f& C = src_covs[i];
+      const float tr = C(0, 0) + C(1, 1) + C(2, 2);
+      if (!(tr > 0.f) || !(tr < 1.f) || C(0, 1) != C(1, 0) || C(0, 2) != C(2, 0) || C(1, 2) != C(2, 1)) ++bad_cov;
+    }
+    std::printf("ComputeCovariances: %zu matrices, %d not symmetric / not positive\n", src_covs.size(), bad_cov);
+    if (bad_cov) ++failures;
+
+    Eigen::Vector3f src_mean;
+    rs_tracker::ComputeCentroid(src, &src_mean);
+    double ref[3] = {0, 0, 0};
+    for (int i = 0; i < n; ++i) for (int a = 0; a < 3; ++a) ref[a] += s[3 * i + a];
+    float ec = 0.f;
+    for (int a = 0; a < 3; ++a) ec = std::fmax(ec, std::fabs(src_mean(a) - (float)(ref[a] / n)));
+    std::printf("ComputeCentroid error %.3e\n", ec);
+    if (!(ec < 1e-6f)) ++failures;
   }
   std::printf("failures %d\n", failures);
   return failures;

@@ -74,3 +74,47 @@ def test_compute_covariances(al):
             assert np.median(err) < 1e-4 and (err < 1e-2).mean() > 0.97, (np.median(err), (err < 1e-2).mean())
             ev = np.linalg.eigvalsh(got.astype(np.float64))
             assert np.allclose(ev[:, 0], 1e-2, atol=1e-4) and np.allclose(ev[:, 1:], 1.0, atol=1e-4)
+
+
+def test_compute_centroid(al):
+    """ComputeCentroid (point_cloud_utils.cpp:92-98): the reference sums sequentially in fp32, the device in fp64 in a
+    fixed order; both within fp32 round-off of the exact mean, and the device result repeats bit for bit."""
+    for cloud in (GOLD["src"], depth_cloud(0), depth_cloud(2, 0.0), GOLD["dst"][:1]):
+        got = al.cloud_centroid(cloud)
+        exact = cloud.astype(np.float64).mean(axis=0)
+        scale = np.abs(cloud).max()
+        assert np.abs(got - exact).max() <= 1e-7 * scale + 1e-12
+        assert np.array_equal(got, al.cloud_centroid(cloud))
+        if HAVE_REF:
+            assert np.abs(got - O.ref_centroid(cloud)).max() <= 1e-4 * scale      # the reference's own fp32 running sum
+    with pytest.raises(Exception):
+        al.cloud_centroid(np.zeros((0, 3), np.float32))
+
+
+def test_orient_normals(al):
+    """OrientNormals (point_cloud_utils.cpp:205-216) on caller-supplied normals: the flips of the compiled reference,
+    except where the ray is perpendicular to the normal to within rounding (the sign of a sum of three products)."""
+    rng = np.random.default_rng(5)
+    cloud = depth_cloud(1)
+    nrm = rng.normal(size=cloud.shape).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm[3] = 0.0                                              # a zero normal is left alone (dot = 0 is not > 0)
+    for vp in ((0.0, 0.0, 0.0), (0.3, -0.2, 1.5)):
+        got = al.orient_normals(cloud, vp, nrm)
+        dot = ((cloud.astype(np.float64) - np.asarray(vp)) * nrm).sum(1)
+        want = np.where((dot > 0)[:, None], -nrm, nrm)
+        clear = np.abs(dot) > 1e-5
+        assert clear.mean() > 0.99
+        assert np.array_equal(got[clear], want[clear])
+        assert np.array_equal(np.abs(got), np.abs(nrm))      # only signs change
+        assert (((cloud - np.asarray(vp, np.float32)) * got).sum(1)[clear] <= 0).all()
+        if HAVE_REF:
+            assert np.array_equal(got[clear], O.ref_orient_normals(cloud, vp, nrm)[clear])
+    # ComputeNormals + OrientNormals in two calls == the fused rst_cloud_normals with that viewpoint
+    vp = (0.3, -0.2, 1.5)
+    n0 = al.cloud_normals(cloud, 16)
+    n1 = al.cloud_normals(cloud, 16, viewpoint=vp)
+    n2 = al.orient_normals(cloud, vp, n0)
+    d = ((cloud.astype(np.float64) - np.asarray(vp)) * n1).sum(1)
+    clear = np.abs(d) > 1e-5
+    assert np.array_equal(n2[clear], n1[clear])
