@@ -347,6 +347,48 @@ inline void OrientNormals(const Cloud& cloud, const Eigen::Vector3f& viewpoint, 
   OrientNormals(DefaultAlignContext(), cloud, viewpoint.data(), normals);
 }
 
+/// float ComputeAlignment(src, dst, src_covs, dst_covs, dst_indices, seed, transform)  align_gicp.hpp:15-21 /
+/// align_gicp.cpp:41-117: the minimiser of the Huber(0.5) GICP cost over the given correspondences, from `seed`;
+/// returns the final cost. kGicpInnerIterations Levenberg-Marquardt steps stand where the reference runs Ceres.
+#ifndef RS_TRACKER_GICP_INNER_ITERATIONS
+#define RS_TRACKER_GICP_INNER_ITERATIONS 32
+#endif
+template <class Cloud>
+inline float ComputeAlignment(const Cloud& src, const Cloud& dst, const std::vector<Eigen::Matrix3f>& src_covs,
+                              const std::vector<Eigen::Matrix3f>& dst_covs, const std::vector<int>& dst_indices,
+                              const Eigen::Isometry3f& seed, Eigen::Isometry3f* const transform) {
+  const rst_cloud s{src.GetPtr(), static_cast<std::int32_t>(src.GetNumPoints())};
+  const rst_cloud d{dst.GetPtr(), static_cast<std::int32_t>(dst.GetNumPoints())};
+  if (src_covs.size() < static_cast<std::size_t>(s.n) || dst_covs.size() < static_cast<std::size_t>(d.n) ||
+      dst_indices.size() < static_cast<std::size_t>(s.n))
+    return std::numeric_limits<float>::infinity();
+  std::vector<float> sc(9 * static_cast<std::size_t>(s.n)), dc(9 * static_cast<std::size_t>(d.n));
+  for (std::size_t i = 0; i < static_cast<std::size_t>(s.n); ++i) std::memcpy(sc.data() + 9 * i, src_covs[i].data(), sizeof(float) * 9);
+  for (std::size_t i = 0; i < static_cast<std::size_t>(d.n); ++i) std::memcpy(dc.data() + 9 * i, dst_covs[i].data(), sizeof(float) * 9);
+  Pose p = detail::ToPose(seed);
+  rst_gicp_stats st{};
+  const int rc = rst_gicp_minimize(DefaultAlignContext().get(), &s, &d, sc.data(), dc.data(), dst_indices.data(),
+                                   RS_TRACKER_GICP_INNER_ITERATIONS, /*huber_delta=*/0.5f, p.m.data(), &st);
+  if (rc != RST_OK) return std::numeric_limits<float>::infinity();
+  detail::FromPose(p, transform);
+  return static_cast<float>(st.cost);
+}
+
+/// float ComputeAlignment(src, dst, transform)  align_gicp.hpp:23-25 / align_gicp.cpp:119-163 (rs_tracker.cpp:87,
+/// rs_replay_app.cpp:253): sample covariances, 16 rounds of { FindCorrespondences; minimise }, from the identity.
+template <class Cloud>
+inline float ComputeAlignment(const Cloud& src, const Cloud& dst, Eigen::Isometry3f* const transform) {
+  const rst_cloud s{src.GetPtr(), static_cast<std::int32_t>(src.GetNumPoints())};
+  const rst_cloud d{dst.GetPtr(), static_cast<std::int32_t>(dst.GetNumPoints())};
+  Pose p;   // the reference always starts from the identity (:147)
+  rst_gicp_stats st{};
+  const int rc = rst_gicp_align(DefaultAlignContext().get(), &s, &d, /*max_outer=*/16, /*inner_iters=*/8, /*huber_delta=*/0.5f,
+                                /*use_gicp_covariances=*/0, /*grid_cell=*/0.f, p.m.data(), &st);
+  if (rc != RST_OK) return std::numeric_limits<float>::infinity();   // the reference's answer to a non-finite estimate (:145-150)
+  detail::FromPose(p, transform);
+  return static_cast<float>(st.cost);
+}
+
 /// Drop-in signature for the reference's call sites (rs_replay_app.cpp:251, rs_align_app.cpp:303).
 inline bool AlignRgbd(AlignContext& ctx, const DepthFrame& src, const DepthFrame& dst, const Eigen::Matrix3f& K,
                       const AlignParams& params, Eigen::Isometry3f* const transform, AlignStats* const stats = nullptr) {

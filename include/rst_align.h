@@ -439,6 +439,16 @@ int32_t rst_gicp_evaluate(rst_ctx* ctx, const rst_cloud* src, const rst_cloud* d
                           const int32_t* dst_indices, const float* pose, float huber_delta, float* residuals_out,
                           rst_gicp_stats* stats_out);
 
+/* The 7-argument ComputeAlignment (align_gicp.cpp:41-117) itself: the pose that minimises the robustified cost above
+ * for GIVEN covariances and correspondences (layouts as rst_gicp_evaluate), starting from the seed in pose_inout. The
+ * reference hands the problem to Ceres (Levenberg-Marquardt, at most 1024 iterations; absent, out of scope): here
+ * `max_iters` Levenberg-Marquardt steps on the normal equations above, a step that raises the cost being rejected
+ * (0 = evaluate the seed only). stats_out (nullable): cost (= ceres' final_cost, the function's return value), A, b and
+ * count at the returned pose. */
+int32_t rst_gicp_minimize(rst_ctx* ctx, const rst_cloud* src, const rst_cloud* dst, const float* src_covs, const float* dst_covs,
+                          const int32_t* dst_indices, int32_t max_iters, float huber_delta, float* pose_inout,
+                          rst_gicp_stats* stats_out);
+
 /* The 3-argument ComputeAlignment (align_gicp.cpp:119-163): covariances of both clouds (ComputeCovariances;
  * use_gicp_covariances = 0 is what the reference passes), then `max_outer` (reference: 16) rounds of
  * { FindCorrespondences(dst, pose * src); minimise the robustified cost over the fixed correspondences }. The reference

@@ -78,7 +78,7 @@ ALIGN_SYMBOLS = [
     "rst_copy_results_device", "rst_profile_enable", "rst_profile_read", "rst_set_pipeline_chunk", "rst_set_stream_split", "rst_align_pairs_async", "rst_align_sequence_async", "rst_wait", "rst_icp3d_pairs", "rst_solve_kabsch", "rst_cloud_normals", "rst_icp3d_depth", "rst_icp3d_read_cloud",
     "rst_set_schedule", "rst_set_cluster_size", "rst_max_active_clusters",
     "rst_find_correspondences", "rst_cloud_covariances", "rst_downsample_voxel", "rst_remove_nans", "rst_cloud_centroid", "rst_orient_normals",
-    "rst_gicp_evaluate", "rst_gicp_align", "rst_set_graph_max_pairs", "rst_set_icp3d_cluster", "rst_set_icp3d_cache", "rst_icp3d_cache_stats", "rst_set_icp3d_fixed_point_skip", "rst_icp3d_iteration_stats",
+    "rst_gicp_evaluate", "rst_gicp_minimize", "rst_gicp_align", "rst_set_graph_max_pairs", "rst_set_icp3d_cluster", "rst_set_icp3d_cache", "rst_icp3d_cache_stats", "rst_set_icp3d_fixed_point_skip", "rst_icp3d_iteration_stats",
 ]
 
 _align = None
@@ -147,6 +147,9 @@ def align_lib() -> C.CDLL:
         lib.rst_cloud_centroid.restype = C.c_int32
         lib.rst_orient_normals.argtypes = [C.c_void_p, P(Cloud), C.c_void_p, C.c_void_p]
         lib.rst_orient_normals.restype = C.c_int32
+        lib.rst_gicp_minimize.argtypes = [C.c_void_p, P(Cloud), P(Cloud), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_float,
+                                          C.c_void_p, P(GicpStats)]
+        lib.rst_gicp_minimize.restype = C.c_int32
         lib.rst_gicp_evaluate.argtypes = [C.c_void_p, P(Cloud), P(Cloud), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float,
                                           C.c_void_p, P(GicpStats)]
         lib.rst_gicp_evaluate.restype = C.c_int32

@@ -246,6 +246,19 @@ class Aligner:
                                                 pose.ctypes.data, huber, res.ctypes.data if res is not None else None, C.byref(st)))
         return res, st
 
+    def gicp_minimize(self, src, dst, src_covs, dst_covs, dst_indices, T0=None, max_iters: int = 32, huber: float = 0.5):
+        """The 7-argument ComputeAlignment (align_gicp.cpp:41-117) on the GPU: minimises the robustified GICP cost over the
+        pose for given covariances and correspondences, from the seed T0. Returns (pose 4x4, GicpStats at that pose)."""
+        S, D = np.ascontiguousarray(src, dtype=np.float32), np.ascontiguousarray(dst, dtype=np.float32)
+        cs_, cd_ = np.ascontiguousarray(src_covs, dtype=np.float32), np.ascontiguousarray(dst_covs, dtype=np.float32)
+        idx = np.ascontiguousarray(dst_indices, dtype=np.int32)
+        pose = pose_to_cm(np.eye(4) if T0 is None else T0).copy()
+        st = N.GicpStats()
+        a, b = N.Cloud(S.ctypes.data, len(S)), N.Cloud(D.ctypes.data, len(D))
+        self._check(self._lib.rst_gicp_minimize(self._ctx, C.byref(a), C.byref(b), cs_.ctypes.data, cd_.ctypes.data, idx.ctypes.data,
+                                                max_iters, huber, pose.ctypes.data, C.byref(st)))
+        return cm_to_pose(pose), st
+
     def gicp_align(self, src, dst, max_outer: int = 16, inner_iters: int = 4, huber: float = 0.5, use_gicp_covariances: bool = False,
                    T0=None, grid_cell: float = 0.0):
         """The 3-argument ComputeAlignment (align_gicp.cpp:119-163) on the GPU. Returns (pose 4x4, GicpStats)."""

@@ -2293,6 +2293,63 @@ extern "C" int32_t rst_gicp_evaluate(rst_ctx* c, const rst_cloud* src, const rst
   return RST_OK;
 }
 
+/* The 7-argument ComputeAlignment (align_gicp.cpp:41-117): minimise the robustified cost over the pose for GIVEN
+ * covariances and correspondences, starting from the seed. */
+extern "C" int32_t rst_gicp_minimize(rst_ctx* c, const rst_cloud* src, const rst_cloud* dst, const float* src_covs, const float* dst_covs,
+                                     const int32_t* dst_indices, int32_t max_iters, float huber_delta, float* pose_inout,
+                                     rst_gicp_stats* stats_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  CloudCall k(c);
+  if (!cloud_ok(src) || !cloud_ok(dst) || !src_covs || !dst_covs || !dst_indices || !pose_inout || max_iters < 0)
+    return k.fail(RST_ERR_INVALID_ARG, "null argument / bad cloud / negative iteration count");
+  if (stats_out) std::memset(stats_out, 0, sizeof(*stats_out));
+  if (src->n == 0 || dst->n == 0) return RST_OK;   // no residual block: the seed is the minimiser
+  CLOUD_TRY(k.begin());
+  const size_t n = (size_t)src->n, m = (size_t)dst->n;
+  const int n_blocks = (int)((n + kGicpThreads - 1) / kGicpThreads);
+  const size_t o_src = k.take(12 * n), o_dst = k.take(12 * m), o_sc = k.take(36 * n), o_dc = k.take(36 * m), o_idx = k.take(4 * n);
+  const size_t o_state = k.take(sizeof(GicpState));
+  const size_t upload = k.off;
+  const size_t host_end = k.off;
+  const size_t o_part = k.take(sizeof(double) * kGicpSums * (size_t)n_blocks);
+  CLOUD_TRY(k.commit(host_end));
+  std::memcpy(k.H + o_src, src->xyz, 12 * n); std::memcpy(k.H + o_dst, dst->xyz, 12 * m);
+  std::memcpy(k.H + o_sc, src_covs, 36 * n); std::memcpy(k.H + o_dc, dst_covs, 36 * m);
+  std::memcpy(k.H + o_idx, dst_indices, 4 * n);
+  GicpState* hs = reinterpret_cast<GicpState*>(k.H + o_state);
+  std::memset(hs, 0, sizeof(*hs));
+  std::memcpy(hs->pose_cm, pose_inout, 64);
+  for (int r = 0; r < 3; ++r) { for (int cc = 0; cc < 3; ++cc) hs->Rt[3 * r + cc] = pose_inout[r + 4 * cc]; hs->Rt[9 + r] = pose_inout[12 + r]; }
+  hs->lambda = 1e-4;
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.D, k.H, upload, cudaMemcpyHostToDevice, k.stream), "H2D"));
+  GicpState* ds = reinterpret_cast<GicpState*>(k.D + o_state);
+  const float* d_src = reinterpret_cast<const float*>(k.D + o_src);
+  const float* d_dst = reinterpret_cast<const float*>(k.D + o_dst);
+  const float* d_sc = reinterpret_cast<const float*>(k.D + o_sc);
+  const float* d_dc = reinterpret_cast<const float*>(k.D + o_dc);
+  const int* d_idx = reinterpret_cast<const int*>(k.D + o_idx);
+  double* d_part = reinterpret_cast<double*>(k.D + o_part);
+  // max_iters Levenberg-Marquardt steps (the first evaluation is accepted unconditionally), then the statistics of the
+  // best pose: mode 3 falls back to the last accepted pose when the final step made the cost worse
+  for (int it = 0; it <= max_iters; ++it) {
+    k_gicp_residuals<<<n_blocks, kGicpThreads, 0, k.stream>>>(d_src, d_dst, d_sc, d_dc, d_idx, (int)n, (int)m, ds->pose_cm, huber_delta, nullptr, d_part);
+    k_gicp_finish<<<1, 32, 0, k.stream>>>(d_part, n_blocks, ds, it == max_iters ? 3 : (it == 0 ? 2 : 1));
+  }
+  CLOUD_TRY(k.cuda(cudaGetLastError(), "launch"));
+  rst::ctx_count_launches(c, 2 * (max_iters + 1));
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.H + o_state, k.D + o_state, sizeof(GicpState), cudaMemcpyDeviceToHost, k.stream), "D2H"));
+  CLOUD_TRY(k.cuda(cudaStreamSynchronize(k.stream), "sync"));
+  std::memcpy(pose_inout, hs->pose_cm, 64);
+  pose_inout[3] = pose_inout[7] = pose_inout[11] = 0.f; pose_inout[15] = 1.f;
+  if (stats_out) {
+    for (int i = 0; i < 21; ++i) stats_out->A[i] = hs->sums[i];
+    for (int i = 0; i < 6; ++i) stats_out->b[i] = hs->sums[21 + i];
+    stats_out->cost = hs->sums[27];
+    stats_out->count = (int32_t)hs->sums[28];
+  }
+  return RST_OK;
+}
+
 extern "C" int32_t rst_gicp_align(rst_ctx* c, const rst_cloud* src, const rst_cloud* dst, int32_t max_outer, int32_t inner_iters,
                                   float huber_delta, int32_t use_gicp_covariances, float grid_cell, float* pose_inout, rst_gicp_stats* stats_out) {
   if (!c) return RST_ERR_INVALID_ARG;

@@ -11,6 +11,8 @@
 //                               OrientNormals(cloud_transformed, viewpoint, &normals)
 //   align_gicp.cpp:120-121      std::vector<Eigen::Matrix3f> src_covs(src.GetNumPoints()); ComputeCovariances(*src_tree, src, &src_covs, false)
 //   point_cloud_utils.hpp:16    ComputeCentroid(cloud, &centroid)   (align_icp.cpp:86)
+//   align_gicp.cpp:141-143      cost = ComputeAlignment(src, dst, src_covs, dst_covs, nn_indices, estimate, &delta_xfm)
+//   rs_tracker.cpp:87           rs_tracker::ComputeAlignment(prev_cloud, curr_cloud, &transform)
 #include <cmath>
 #include <cstdio>
 #include <memory>
@@ -141,6 +143,42 @@ int main() {
     }
     std::printf("ComputeCovariances: %zu matrices, %d not symmetric / not positive\n", src_covs.size(), bad_cov);
     if (bad_cov) ++failures;
+
+    // align_gicp.cpp:122-143 (one round) and rs_tracker.cpp:87
+    {
+      const rs_tracker::Cloud3f& dst = dst_cloud;
+      std::shared_ptr<rs_tracker::KDTree3f> dst_tree = std::make_shared<rs_tracker::KDTree3f>(std::cref(dst), 10);
+      std::vector<Eigen::Matrix3f> dst_covs(dst.GetNumPoints());
+      rs_tracker::ComputeCovariances(*dst_tree, dst, &dst_covs, false);
+      // rs_tracker.cpp:87
+      const rs_tracker::Cloud3f& prev_cloud = src_cloud;
+      const rs_tracker::Cloud3f& curr_cloud = dst_cloud;
+      Eigen::Isometry3f transform = Eigen::Isometry3f::Identity();
+      const float c3 =
+        rs_tracker::ComputeAlignment(prev_cloud, curr_cloud, &transform);
+      const float e3 = translation_error(transform, t);
+      std::printf("ComputeAlignment (3 arguments): cost %.4e, translation error %.3e\n", c3, e3);
+      if (!std::isfinite(c3) || !(e3 < 0.02f)) ++failures;
+
+      // one more round of the loop of align_gicp.cpp:128-159 from that estimate
+      Eigen::Isometry3f estimate = transform;
+      rs_tracker::Cloud3f tmp;
+      tmp.SetNumPoints(src.GetNumPoints());
+      const float* E = estimate.matrix().data();
+      for (int i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a)
+          tmp.GetPtr()[3 * i + a] = E[a] * s[3 * i] + E[4 + a] * s[3 * i + 1] + E[8 + a] * s[3 * i + 2] + E[12 + a];
+      std::vector<int> nn_indices;
+      std::vector<float> nn_sq_dists;
+      rs_tracker::FindCorrespondences(*dst_tree, tmp, &nn_indices, &nn_sq_dists);
+      float cost{0};
+      Eigen::Isometry3f delta_xfm = Eigen::Isometry3f::Identity();
+      cost = rs_tracker::ComputeAlignment(src, dst, src_covs, dst_covs, nn_indices, estimate,
+                              &delta_xfm);
+      const float e7 = translation_error(delta_xfm, t);
+      std::printf("ComputeAlignment (7 arguments): cost %.4e, translation error %.3e\n", cost, e7);
+      if (!(cost >= 0.f) || !std::isfinite(cost) || !(e7 < e3 + 1e-3f)) ++failures;
+    }
 
     Eigen::Vector3f src_mean;
     rs_tracker::ComputeCentroid(src, &src_mean);

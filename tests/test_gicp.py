@@ -108,3 +108,45 @@ def test_gpu_gicp_alignment_recovers_the_motion():
         assert np.array_equal(T, T2)                            # deterministic
     finally:
         al.close()
+
+
+@pytest.mark.gpu
+def test_gpu_gicp_minimize_over_fixed_correspondences():
+    """The 7-argument ComputeAlignment (align_gicp.cpp:41-117): for given covariances and correspondences the returned
+    pose lowers the cost of the seed, is a stationary point of it (the Gauss-Newton step there is negligible), its
+    statistics are those of rst_gicp_evaluate at that pose, and 16 rounds of { FindCorrespondences; minimise } driven
+    from the host reproduce the 3-argument form."""
+    from realsensetracker_b200 import Aligner
+    s, d = clouds()
+    al = Aligner(16, 16, 2, 1)
+
+    def gn_step(st):
+        A = np.zeros((6, 6)); A[np.triu_indices(6)] = np.array(st.A[:]); A = A + A.T - np.diag(np.diag(A))
+        return np.linalg.solve(A, -np.array(st.b[:]))
+
+    try:
+        Cs, Cd = al.cloud_covariances(s, True), al.cloud_covariances(d, True)
+        idx, _ = al.find_correspondences(d, s)
+        I = np.eye(4)
+        _, st0 = al.gicp_evaluate(s, d, Cs, Cd, idx, I, huber=0.5, want_residuals=False)
+        T0, stz = al.gicp_minimize(s, d, Cs, Cd, idx, T0=I, max_iters=0)
+        assert np.array_equal(T0, I) and stz.cost == st0.cost and stz.count == st0.count == len(s)
+        T1, st1 = al.gicp_minimize(s, d, Cs, Cd, idx, T0=I, max_iters=32)
+        assert st1.count == len(s) and st1.cost < st0.cost
+        _, st_at = al.gicp_evaluate(s, d, Cs, Cd, idx, T1, huber=0.5, want_residuals=False)
+        assert np.isclose(st_at.cost, st1.cost, rtol=1e-6)
+        x0, x1 = np.linalg.norm(gn_step(st0)), np.linalg.norm(gn_step(st_at))
+        print(f"gicp minimise: cost {st0.cost:.4f} -> {st1.cost:.4f}, Gauss-Newton step {x0:.2e} -> {x1:.2e}")
+        assert x1 < 1e-3 and x1 < 0.2 * x0
+        T2, st2 = al.gicp_minimize(s, d, Cs, Cd, idx, T0=I, max_iters=32)
+        assert np.array_equal(T1, T2) and st2.cost == st1.cost             # deterministic
+        # the 3-argument form = this call inside the correspondence loop
+        T = I.copy()
+        for _ in range(16):
+            idx_k, _ = al.find_correspondences(d, (s.astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32))
+            T, _ = al.gicp_minimize(s, d, Cs, Cd, idx_k, T0=T, max_iters=4)
+        Ta, _ = al.gicp_align(s, d, max_outer=16, inner_iters=4, huber=0.5, use_gicp_covariances=True)
+        dt, dr = synth.pose_error(T, Ta)
+        assert dt < 1e-3 and dr < 1e-3, (dt, dr)
+    finally:
+        al.close()
