@@ -231,6 +231,14 @@ inline void ComputeCentroid(AlignContext& ctx, const Cloud& cloud, float* const 
     centroid_xyz[0] = centroid_xyz[1] = centroid_xyz[2] = std::numeric_limits<float>::quiet_NaN();   // 0 / 0 in the reference
 }
 
+/// void ComputeExtents(cloud, &box)  point_cloud_utils.cpp:26-32; lo_xyz / hi_xyz: 3 floats each (empty cloud: FLT_MAX / -FLT_MAX).
+template <class Cloud>
+inline void ComputeExtents(AlignContext& ctx, const Cloud& cloud, float* const lo_xyz, float* const hi_xyz) {
+  const rst_cloud c{cloud.GetPtr(), static_cast<std::int32_t>(cloud.GetNumPoints())};
+  if (rst_cloud_extents(ctx.get(), &c, lo_xyz, hi_xyz) != RST_OK)
+    for (int a = 0; a < 3; ++a) { lo_xyz[a] = std::numeric_limits<float>::max(); hi_xyz[a] = std::numeric_limits<float>::lowest(); }
+}
+
 /// void ComputeCovariances(tree, cloud, &covs, use_gicp)  point_cloud_utils.cpp:100-161; covs_9n: n x 9 floats
 /// (symmetric 3x3 each, so row- and column-major agree).
 template <class Cloud>
@@ -324,6 +332,17 @@ inline auto FindCorrespondences(const Tree& tree, const Cloud& source, std::vect
 template <class Cloud>
 inline void ComputeCentroid(const Cloud& cloud, Eigen::Vector3f* const centroid) {
   ComputeCentroid(DefaultAlignContext(), cloud, centroid->data());
+}
+/// void ComputeExtents(const Cloud3f& cloud, Eigen::AlignedBox3f* const box)  point_cloud_utils.cpp:26-32
+template <class Cloud, class Box>
+inline auto ComputeExtents(const Cloud& cloud, Box* const box) -> decltype(box->setEmpty(), void()) {
+  float lo[3], hi[3];
+  ComputeExtents(DefaultAlignContext(), cloud, lo, hi);
+  box->setEmpty();
+  if (lo[0] <= hi[0] && lo[1] <= hi[1] && lo[2] <= hi[2]) {
+    box->extend(Eigen::Vector3f(lo[0], lo[1], lo[2]));
+    box->extend(Eigen::Vector3f(hi[0], hi[1], hi[2]));
+  }
 }
 /// void ComputeCovariances(const KDTree3f& tree, const Cloud3f& cloud, std::vector<Eigen::Matrix3f>* const covs,
 /// const bool use_gicp)  (align_gicp.cpp:121,123); the tree is accepted and not used (the GPU grids the cloud itself).

@@ -414,6 +414,10 @@ int32_t rst_remove_nans(rst_ctx* ctx, const rst_cloud* cloud_in, float* xyz_out,
  *   (the reference sums sequentially in fp32: equal to fp32 round-off of that sum). centroid_out: 3 floats. An empty
  *   cloud is RST_ERR_INVALID_ARG (the reference divides by zero). */
 int32_t rst_cloud_centroid(rst_ctx* ctx, const rst_cloud* cloud, float* centroid_out);
+/* ComputeExtents(cloud, &box)  point_cloud_utils.cpp:26-32: axis-aligned bounding box, lo_out / hi_out: 3 floats each
+ *   (bit-exact: min and max are exact). An empty cloud gives Eigen's empty box (lo = FLT_MAX, hi = -FLT_MAX); NaN
+ *   coordinates are ignored, infinite ones are not. */
+int32_t rst_cloud_extents(rst_ctx* ctx, const rst_cloud* cloud, float* lo_out, float* hi_out);
 /* OrientNormals(cloud, viewpoint, &normals)  point_cloud_utils.cpp:205-216: normals_inout[i] is negated where
  *   (cloud[i] - viewpoint) . normals_inout[i] > 0. rst_cloud_normals() already orients its output; this is for normals
  *   that come from elsewhere or for a second viewpoint. viewpoint: 3 floats; normals_inout: n x 3 floats. */

@@ -414,6 +414,14 @@ def ref_normals(pts, k=16, viewpoint=(0.0, 0.0, 0.0)):
     return out
 
 
+def ref_extents(pts):
+    """ComputeExtents (point_cloud_utils.cpp:26-32) through the compiled reference: (lo [3], hi [3]) float32."""
+    p = _f32(pts)
+    lo, hi = np.empty(3, dtype=np.float32), np.empty(3, dtype=np.float32)
+    ref_lib().ref_extents(p.ctypes.data_as(C.c_void_p), C.c_int32(len(p)), lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p))
+    return lo, hi
+
+
 def ref_orient_normals(pts, viewpoint, normals):
     """OrientNormals (point_cloud_utils.cpp:205-216) through the compiled reference: a flipped copy of `normals`."""
     p = _f32(pts)

@@ -14,6 +14,8 @@ static void to_cloud(const float* xyz, int n, Cloud3f* c) { c->SetNumPoints(n); 
 static void to_pose(const float* T, Eigen::Isometry3f* x) { std::memcpy(x->matrix().data(), T, sizeof(float) * 16); }
 static void from_pose(const Eigen::Isometry3f& x, float* T) { std::memcpy(T, x.matrix().data(), sizeof(float) * 16); }
 
+namespace rs_tracker { void ComputeExtents(const Cloud3f& cloud, Eigen::AlignedBox3f* const box); }
+
 extern "C" {
 int ref_align_icp3d(const float* src, int n, const float* dst, int m, int max_iter, float* T) {
   Cloud3f s, d; to_cloud(src, n, &s); to_cloud(dst, m, &d);
@@ -106,6 +108,15 @@ void ref_normals(const float* pts, int n, int k, const float* viewpoint, float* 
   rs_tracker::ComputeNormals(s, tree, (float)k, &nrm);
   rs_tracker::OrientNormals(s, Eigen::Vector3f(viewpoint[0], viewpoint[1], viewpoint[2]), &nrm);
   std::memcpy(out, nrm.GetPtr(), sizeof(float) * 3 * n);
+}
+
+// ComputeExtents (point_cloud_utils.cpp:26-32; defined there, declared in no header)
+void ref_extents(const float* pts, int n, float* lo, float* hi) {
+  Cloud3f s; to_cloud(pts, n, &s);
+  Eigen::AlignedBox3f box;
+  rs_tracker::ComputeExtents(s, &box);
+  const Eigen::Vector3f a = box.min(), b = box.max();
+  for (int i = 0; i < 3; ++i) { lo[i] = a[i]; hi[i] = b[i]; }
 }
 
 // OrientNormals alone (point_cloud_utils.cpp:205-216) on caller-supplied normals, in place

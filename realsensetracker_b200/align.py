@@ -198,6 +198,14 @@ class Aligner:
         self._check(self._lib.rst_cloud_centroid(self._ctx, C.byref(cs), out.ctypes.data))
         return out
 
+    def cloud_extents(self, cloud):
+        """ComputeExtents(cloud, &box) (point_cloud_utils.cpp:26-32) on the GPU: (lo [3], hi [3]) float32."""
+        S = np.ascontiguousarray(cloud, dtype=np.float32)
+        lo, hi = np.empty(3, dtype=np.float32), np.empty(3, dtype=np.float32)
+        cs = N.Cloud(S.ctypes.data, len(S))
+        self._check(self._lib.rst_cloud_extents(self._ctx, C.byref(cs), lo.ctypes.data, hi.ctypes.data))
+        return lo, hi
+
     def orient_normals(self, cloud, viewpoint, normals) -> np.ndarray:
         """OrientNormals(cloud, viewpoint, &normals) (point_cloud_utils.cpp:205-216) on the GPU: a flipped copy of `normals`."""
         S = np.ascontiguousarray(cloud, dtype=np.float32)

@@ -1289,6 +1289,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_centroid(const float* __restric
   }
 }
 
+// ComputeExtents (point_cloud_utils.cpp:26-32): axis-aligned bounding box of the cloud, out = {lo xyz, hi xyz}; the empty
+// box is {FLT_MAX.., -FLT_MAX..} (Eigen::AlignedBox::setEmpty). min / max are exact, so any order gives the same bits.
+__global__ void __launch_bounds__(kThreads, 1) k_extents(const float* __restrict__ pts, int n, float* __restrict__ out) {
+  __shared__ float s_lohi[kWarps][6];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int j = tid; j < n; j += kThreads)
+    for (int a = 0; a < 3; ++a) { const float v = pts[3 * j + a]; lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
+  for (int a = 0; a < 3; ++a)
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+  if (lane == 0) for (int a = 0; a < 3; ++a) { s_lohi[warp][a] = lo[a]; s_lohi[warp][3 + a] = hi[a]; }
+  __syncthreads();
+  if (tid < 6) {
+    float v = s_lohi[0][tid];
+    for (int w = 1; w < kWarps; ++w) v = tid < 3 ? fminf(v, s_lohi[w][tid]) : fmaxf(v, s_lohi[w][tid]);
+    out[tid] = v;
+  }
+}
+
 // OrientNormals (point_cloud_utils.cpp:205-216): a normal that points along the viewing ray p - viewpoint is negated.
 __global__ void __launch_bounds__(256) k_orient_normals(const float* __restrict__ pts, int n, float vx, float vy, float vz,
                                                         float* __restrict__ normals) {
@@ -2160,6 +2182,32 @@ extern "C" int32_t rst_cloud_centroid(rst_ctx* c, const rst_cloud* cloud, float*
   CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.H + o_cen, k.D + o_cen, 12, cudaMemcpyDeviceToHost, k.stream), "D2H"));
   CLOUD_TRY(k.cuda(cudaStreamSynchronize(k.stream), "sync"));
   std::memcpy(centroid_out, k.H + o_cen, 12);
+  return RST_OK;
+}
+
+/* void ComputeExtents(cloud, &box)  point_cloud_utils.cpp:26-32 */
+extern "C" int32_t rst_cloud_extents(rst_ctx* c, const rst_cloud* cloud, float* lo_out, float* hi_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  CloudCall k(c);
+  if (!cloud_ok(cloud) || !lo_out || !hi_out) return k.fail(RST_ERR_INVALID_ARG, "null argument / bad cloud");
+  for (int a = 0; a < 3; ++a) { lo_out[a] = FLT_MAX; hi_out[a] = -FLT_MAX; }   // the empty box
+  if (cloud->n == 0) return RST_OK;
+  CLOUD_TRY(k.begin());
+  const size_t n = (size_t)cloud->n;
+  const size_t o_pts = k.take(12 * n);
+  const size_t upload = k.off;
+  const size_t o_box = k.take(24);
+  const size_t host_end = k.off;
+  CLOUD_TRY(k.commit(host_end));
+  std::memcpy(k.H + o_pts, cloud->xyz, 12 * n);
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.D, k.H, upload, cudaMemcpyHostToDevice, k.stream), "H2D"));
+  k_extents<<<1, kThreads, 0, k.stream>>>(reinterpret_cast<const float*>(k.D + o_pts), (int)n, reinterpret_cast<float*>(k.D + o_box));
+  CLOUD_TRY(k.cuda(cudaGetLastError(), "launch"));
+  rst::ctx_count_launches(c, 1);
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.H + o_box, k.D + o_box, 24, cudaMemcpyDeviceToHost, k.stream), "D2H"));
+  CLOUD_TRY(k.cuda(cudaStreamSynchronize(k.stream), "sync"));
+  std::memcpy(lo_out, k.H + o_box, 12);
+  std::memcpy(hi_out, k.H + o_box + 12, 12);
   return RST_OK;
 }
 

@@ -11,6 +11,7 @@
 //                               OrientNormals(cloud_transformed, viewpoint, &normals)
 //   align_gicp.cpp:120-121      std::vector<Eigen::Matrix3f> src_covs(src.GetNumPoints()); ComputeCovariances(*src_tree, src, &src_covs, false)
 //   point_cloud_utils.hpp:16    ComputeCentroid(cloud, &centroid)   (align_icp.cpp:86)
+//   point_cloud_utils.cpp:26    ComputeExtents(cloud, &box)
 //   align_gicp.cpp:141-143      cost = ComputeAlignment(src, dst, src_covs, dst_covs, nn_indices, estimate, &delta_xfm)
 //   rs_tracker.cpp:87           rs_tracker::ComputeAlignment(prev_cloud, curr_cloud, &transform)
 #include <cmath>
@@ -178,6 +179,19 @@ int main() {
       const float e7 = translation_error(delta_xfm, t);
       std::printf("ComputeAlignment (7 arguments): cost %.4e, translation error %.3e\n", cost, e7);
       if (!(cost >= 0.f) || !std::isfinite(cost) || !(e7 < e3 + 1e-3f)) ++failures;
+    }
+
+    // point_cloud_utils.cpp:26-32
+    {
+      Eigen::AlignedBox3f box;
+      rs_tracker::ComputeExtents(src, &box);
+      float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+      for (int i = 0; i < n; ++i) for (int a = 0; a < 3; ++a) { lo[a] = std::fmin(lo[a], s[3 * i + a]); hi[a] = std::fmax(hi[a], s[3 * i + a]); }
+      const Eigen::Vector3f bl = box.min(), bh = box.max();
+      int bad_box = 0;
+      for (int a = 0; a < 3; ++a) bad_box += (bl[a] != lo[a]) + (bh[a] != hi[a]);
+      std::printf("ComputeExtents: %d of 6 bounds differ\n", bad_box);
+      if (bad_box) ++failures;
     }
 
     Eigen::Vector3f src_mean;

@@ -118,3 +118,20 @@ def test_orient_normals(al):
     d = ((cloud.astype(np.float64) - np.asarray(vp)) * n1).sum(1)
     clear = np.abs(d) > 1e-5
     assert np.array_equal(n2[clear], n1[clear])
+
+
+def test_compute_extents(al):
+    """ComputeExtents (point_cloud_utils.cpp:26-32): bit-exact (min / max are exact), the empty box for an empty cloud."""
+    for cloud in (GOLD["src"], depth_cloud(0), depth_cloud(2, 0.0), GOLD["dst"][:1]):
+        lo, hi = al.cloud_extents(cloud)
+        assert np.array_equal(lo, cloud.min(axis=0)) and np.array_equal(hi, cloud.max(axis=0))
+        if HAVE_REF:
+            rlo, rhi = O.ref_extents(cloud)
+            assert np.array_equal(lo, rlo) and np.array_equal(hi, rhi)
+    lo, hi = al.cloud_extents(np.zeros((0, 3), np.float32))
+    fmax = np.finfo(np.float32).max
+    assert (lo == fmax).all() and (hi == -fmax).all()
+    bad = GOLD["src"].copy(); bad[11] = np.nan
+    lo, hi = al.cloud_extents(bad)
+    keep = np.delete(GOLD["src"], 11, axis=0)
+    assert np.array_equal(lo, keep.min(axis=0)) and np.array_equal(hi, keep.max(axis=0))     # NaN coordinates are ignored
