@@ -265,6 +265,40 @@ inline void OrientNormals(AlignContext& ctx, const Cloud& cloud, const float* co
   if (c.n && normals->GetNumPoints() == cloud.GetNumPoints()) rst_orient_normals(ctx.get(), &c, viewpoint_xyz, normals->GetPtr());
 }
 
+/// The reference's KDTree3f (kdtree.hpp:11-99) on the GPU: built once over a cloud, queried any number of times.
+/// `query` has the signature of KDTreeChoCloudAdaptor::query (kdtree.hpp:51-57); the batched form answers all points of
+/// a cloud in one launch (row i of the n x k outputs = query i).
+class GpuKDTree3f {
+ public:
+  template <class Cloud>
+  GpuKDTree3f(AlignContext& ctx, const Cloud& cloud) : ctx_(ctx) {
+    const rst_cloud c{cloud.GetPtr(), static_cast<std::int32_t>(cloud.GetNumPoints())};
+    if (rst_tree_create(ctx.get(), &c, /*grid_cell=*/0.f, &tree_) != RST_OK) throw std::runtime_error(std::string("rst_tree_create: ") + ctx.LastError());
+  }
+  ~GpuKDTree3f() { rst_tree_destroy(tree_); }
+  GpuKDTree3f(const GpuKDTree3f&) = delete;
+  GpuKDTree3f& operator=(const GpuKDTree3f&) = delete;
+  inline void query(const float* query_point, const std::size_t num_closest, int* out_indices, float* out_distances_sq,
+                    const int /* nChecks_IGNORED */ = 10) const {
+    rst_tree_query(ctx_.get(), tree_, query_point, 1, static_cast<std::int32_t>(num_closest), out_indices, out_distances_sq);
+  }
+  template <class Cloud>
+  inline bool query(const Cloud& queries, const std::size_t num_closest, std::vector<int>* const out_indices,
+                    std::vector<float>* const out_distances_sq) const {
+    const std::size_t n = static_cast<std::size_t>(queries.GetNumPoints());
+    out_indices->assign(n * num_closest, -1);
+    out_distances_sq->assign(n * num_closest, std::numeric_limits<float>::infinity());
+    return rst_tree_query(ctx_.get(), tree_, queries.GetPtr(), static_cast<std::int32_t>(n), static_cast<std::int32_t>(num_closest),
+                          out_indices->data(), out_distances_sq->data()) == RST_OK;
+  }
+  int size() const { return rst_tree_size(tree_); }
+  const rst_tree* get() const { return tree_; }
+
+ private:
+  AlignContext& ctx_;
+  rst_tree* tree_{nullptr};
+};
+
 /// The process-wide context the literal (context-free) signatures below run on: created on first use on CUDA device
 /// RS_TRACKER_ALIGN_DEVICE (default 0). The cloud engine sizes its own device memory per call, so the frame capacity
 /// of this context is minimal; use an explicit AlignContext for the frame-based calls.

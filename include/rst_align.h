@@ -399,6 +399,22 @@ int32_t rst_cloud_normals(rst_ctx* ctx, const rst_cloud* cloud, int32_t k, const
  *   source point in `target`; ties go to the lowest index; a non-finite source point gets index -1, distance +inf. */
 int32_t rst_find_correspondences(rst_ctx* ctx, const rst_cloud* target, const rst_cloud* source, float grid_cell,
                                  int32_t* indices_out, float* sq_dist_out);
+/* KDTree3f (kdtree.hpp:11-99; types.hpp) as a device-resident handle: the search structure of one cloud, built once
+ * (rst_tree_create: upload + one grid-build launch) and queried any number of times without re-uploading or re-building
+ * it — what the reference does with `dst_tree` (align_icp.cpp:163-167) and `tree` (rs_replay_app.cpp:382).
+ * rst_tree_query = KDTree3f::query(point, num_closest, out_indices, out_distances_sq) (kdtree.hpp:51-57) for a batch:
+ * row i of the n_queries x k outputs holds the k nearest points of query i in ascending distance (ties: lower index
+ * first; k = 1 is exactly rst_find_correspondences), squared L2 distances accumulated left to right as nanoflann's
+ * L2_Adaptor. Entries past the cloud's size and all entries of a non-finite query are -1 / +inf. k in [1, 33].
+ * The tree belongs to the device of the context that made it; any context on that device may query it; the cloud is
+ * copied (the caller's buffer is not referenced after rst_tree_create). HOST pointers in and out. */
+typedef struct rst_tree rst_tree;
+int32_t rst_tree_create(rst_ctx* ctx, const rst_cloud* cloud, float grid_cell, rst_tree** tree_out);
+int32_t rst_tree_query(rst_ctx* ctx, const rst_tree* tree, const float* queries_xyz, int32_t n_queries, int32_t k,
+                       int32_t* indices_out, float* sq_dist_out);
+int32_t rst_tree_size(const rst_tree* tree);
+void rst_tree_destroy(rst_tree* tree);
+
 /* ComputeCovariances(tree, cloud, &covs, use_gicp)  point_cloud_utils.cpp:100-161: 32 nearest OTHER points, fp32
  *   centroid + scatter; use_gicp = 0: / 31; use_gicp != 0: singular values replaced by (1, 1, 1e-2) (:139-154).
  *   covs_out: n x 9 floats (row-major symmetric 3x3). */

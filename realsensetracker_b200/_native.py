@@ -77,7 +77,7 @@ ALIGN_SYMBOLS = [
     "rst_level_info", "rst_read_depth", "rst_read_geometry", "rst_read_intensity", "rst_evaluate", "rst_launch_count",
     "rst_copy_results_device", "rst_profile_enable", "rst_profile_read", "rst_set_pipeline_chunk", "rst_set_stream_split", "rst_align_pairs_async", "rst_align_sequence_async", "rst_wait", "rst_icp3d_pairs", "rst_solve_kabsch", "rst_cloud_normals", "rst_icp3d_depth", "rst_icp3d_read_cloud",
     "rst_set_schedule", "rst_set_cluster_size", "rst_max_active_clusters",
-    "rst_find_correspondences", "rst_cloud_covariances", "rst_downsample_voxel", "rst_remove_nans", "rst_cloud_centroid", "rst_orient_normals", "rst_cloud_extents",
+    "rst_find_correspondences", "rst_cloud_covariances", "rst_downsample_voxel", "rst_remove_nans", "rst_cloud_centroid", "rst_orient_normals", "rst_cloud_extents", "rst_tree_create", "rst_tree_query", "rst_tree_size", "rst_tree_destroy",
     "rst_gicp_evaluate", "rst_gicp_minimize", "rst_gicp_align", "rst_set_graph_max_pairs", "rst_set_icp3d_cluster", "rst_set_icp3d_cache", "rst_icp3d_cache_stats", "rst_set_icp3d_fixed_point_skip", "rst_icp3d_iteration_stats",
 ]
 
@@ -145,6 +145,14 @@ def align_lib() -> C.CDLL:
         lib.rst_remove_nans.restype = C.c_int32
         lib.rst_cloud_centroid.argtypes = [C.c_void_p, P(Cloud), C.c_void_p]
         lib.rst_cloud_centroid.restype = C.c_int32
+        lib.rst_tree_create.argtypes = [C.c_void_p, P(Cloud), C.c_float, P(C.c_void_p)]
+        lib.rst_tree_create.restype = C.c_int32
+        lib.rst_tree_query.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        lib.rst_tree_query.restype = C.c_int32
+        lib.rst_tree_size.argtypes = [C.c_void_p]
+        lib.rst_tree_size.restype = C.c_int32
+        lib.rst_tree_destroy.argtypes = [C.c_void_p]
+        lib.rst_tree_destroy.restype = None
         lib.rst_cloud_extents.argtypes = [C.c_void_p, P(Cloud), C.c_void_p, C.c_void_p]
         lib.rst_cloud_extents.restype = C.c_int32
         lib.rst_orient_normals.argtypes = [C.c_void_p, P(Cloud), C.c_void_p, C.c_void_p]

@@ -198,6 +198,24 @@ class Aligner:
         self._check(self._lib.rst_cloud_centroid(self._ctx, C.byref(cs), out.ctypes.data))
         return out
 
+    def tree_create(self, cloud, grid_cell: float = 0.0) -> int:
+        """KDTree3f{cloud} (kdtree.hpp:26-35) on the GPU: an opaque handle of the cloud's device-resident search grid."""
+        S = np.ascontiguousarray(cloud, dtype=np.float32)
+        cs = N.Cloud(S.ctypes.data, len(S))
+        h = C.c_void_p()
+        self._check(self._lib.rst_tree_create(self._ctx, C.byref(cs), grid_cell, C.byref(h)))
+        return h.value
+
+    def tree_query(self, tree: int, queries, k: int = 1):
+        """KDTree3f::query (kdtree.hpp:51-57) for a batch: (indices [n,k] int32, squared distances [n,k] float32)."""
+        Q = np.ascontiguousarray(queries, dtype=np.float32)
+        idx = np.empty((len(Q), k), dtype=np.int32); d2 = np.empty((len(Q), k), dtype=np.float32)
+        self._check(self._lib.rst_tree_query(self._ctx, tree, Q.ctypes.data, len(Q), k, idx.ctypes.data, d2.ctypes.data))
+        return idx, d2
+
+    def tree_destroy(self, tree: int) -> None:
+        self._lib.rst_tree_destroy(tree)
+
     def cloud_extents(self, cloud):
         """ComputeExtents(cloud, &box) (point_cloud_utils.cpp:26-32) on the GPU: (lo [3], hi [3]) float32."""
         S = np.ascontiguousarray(cloud, dtype=np.float32)

@@ -1203,6 +1203,28 @@ __global__ void __launch_bounds__(128) k_nn_query(const Grid* __restrict__ gp, c
   idx[i] = j; d2[i] = d;
 }
 
+// KDTree3f::query(point, num_closest, out_indices, out_distances_sq) (kdtree.hpp:51-57) for a batch of query points:
+// the k nearest points in ascending distance (ties: lower index first), k x nq outputs, row i = query i. Entries past the
+// cloud's size, and every entry of a non-finite query, are index -1 / distance +inf.
+__global__ void __launch_bounds__(128) k_knn_query(const Grid* __restrict__ gp, const int* __restrict__ cell_start,
+                                                   const float4* __restrict__ sorted, int m, const float* __restrict__ q, int nq, int k,
+                                                   int* __restrict__ idx, float* __restrict__ d2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  const Grid g = *gp;
+  const float px = q[3 * i], py = q[3 * i + 1], pz = q[3 * i + 2];
+  float bd[kMaxK]; int bj[kMaxK];
+  int have = 0;
+  if (isfinite(px) && isfinite(py) && isfinite(pz)) {
+    knn_search(g, cell_start, sorted, px, py, pz, k, bd, bj);
+    have = min(k, m);
+  }
+  for (int e = 0; e < k; ++e) {
+    idx[(size_t)i * k + e] = e < have ? bj[e] : -1;
+    d2[(size_t)i * k + e] = e < have ? bd[e] : __int_as_float(0x7f800000);
+  }
+}
+
 // eigen-decomposition of a symmetric 3x3 (cyclic Jacobi, fp32): values descending, vectors in the columns of V
 __device__ void sym_eig3_desc(const float* C, float* val, float* V) {
   float a[9], v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -2127,6 +2149,97 @@ extern "C" int32_t rst_find_correspondences(rst_ctx* c, const rst_cloud* target,
   CLOUD_TRY(k.cuda(cudaStreamSynchronize(k.stream), "sync"));
   std::memcpy(indices_out, k.H + o_idx, 4 * n);
   std::memcpy(sq_dist_out, k.H + o_d2, 4 * n);
+  return RST_OK;
+}
+
+/* KDTree3f (kdtree.hpp:11-99, types.hpp) as a device-resident handle: the search grid of one cloud, built once and
+ * queried any number of times (the reference builds dst_tree once per AlignIcp3d call and queries it 128 x n times,
+ * align_icp.cpp:163-167,112). */
+struct rst_tree {
+  int device = 0;
+  int m = 0;
+  char* d_mem = nullptr;
+  size_t o_grid = 0, o_cs = 0, o_sorted = 0;
+};
+
+extern "C" int32_t rst_tree_create(rst_ctx* c, const rst_cloud* cloud, float grid_cell, rst_tree** tree_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  CloudCall k(c);
+  if (!cloud_ok(cloud) || !tree_out) return k.fail(RST_ERR_INVALID_ARG, "null argument / bad cloud");
+  *tree_out = nullptr;
+  if (cloud->n == 0) return k.fail(RST_ERR_INVALID_ARG, "the cloud is empty");
+  CLOUD_TRY(k.begin());
+  const size_t m = (size_t)cloud->n;
+  const size_t o_stage = k.take(12 * m);
+  CLOUD_TRY(k.commit(k.off));
+  // the tree's own memory: points | grid | cell_start | cell_fill | sorted
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes); return o; };
+  const size_t t_pts = take(12 * m), t_grid = take(sizeof(Grid)), t_cs = take(sizeof(int) * (kCellCap + 1)), t_cf = take(sizeof(int) * kCellCap);
+  const size_t t_sorted = take(sizeof(float4) * m);
+  char* mem = nullptr;
+  CLOUD_TRY(k.cuda(cudaMalloc(&mem, off), "cudaMalloc"));
+  std::memcpy(k.H + o_stage, cloud->xyz, 12 * m);
+  int rc = k.cuda(cudaMemcpyAsync(mem + t_pts, k.H + o_stage, 12 * m, cudaMemcpyHostToDevice, k.stream), "H2D");
+  if (rc == RST_OK) {
+    k_grid_build<<<1, kThreads, 0, k.stream>>>(reinterpret_cast<const float*>(mem + t_pts), (int)m, grid_cell, reinterpret_cast<int*>(mem + t_cs),
+                                               reinterpret_cast<int*>(mem + t_cf), reinterpret_cast<float4*>(mem + t_sorted),
+                                               reinterpret_cast<Grid*>(mem + t_grid));
+    rc = k.cuda(cudaGetLastError(), "launch");
+  }
+  if (rc == RST_OK) { rst::ctx_count_launches(c, 1); rc = k.cuda(cudaStreamSynchronize(k.stream), "sync"); }
+  if (rc != RST_OK) { cudaFree(mem); return rc; }
+  rst_tree* t = new rst_tree();
+  t->device = rst::ctx_device(c); t->m = (int)m; t->d_mem = mem;
+  t->o_grid = t_grid; t->o_cs = t_cs; t->o_sorted = t_sorted;
+  *tree_out = t;
+  return RST_OK;
+}
+
+extern "C" void rst_tree_destroy(rst_tree* tree) {
+  if (!tree) return;
+  int prev = 0;
+  const bool have_prev = cudaGetDevice(&prev) == cudaSuccess;
+  if (cudaSetDevice(tree->device) == cudaSuccess) cudaFree(tree->d_mem);
+  if (have_prev) cudaSetDevice(prev);
+  delete tree;
+}
+
+extern "C" int32_t rst_tree_size(const rst_tree* tree) { return tree ? tree->m : 0; }
+
+extern "C" int32_t rst_tree_query(rst_ctx* c, const rst_tree* tree, const float* queries_xyz, int32_t n_queries, int32_t k_nearest,
+                                  int32_t* indices_out, float* sq_dist_out) {
+  if (!c) return RST_ERR_INVALID_ARG;
+  CloudCall k(c);
+  if (!tree || n_queries < 0 || (n_queries > 0 && (!queries_xyz || !indices_out || !sq_dist_out)))
+    return k.fail(RST_ERR_INVALID_ARG, "null argument");
+  if (k_nearest < 1 || k_nearest > kMaxK) return k.fail(RST_ERR_INVALID_ARG, "k must be in [1, 33]");
+  if (tree->device != rst::ctx_device(c)) return k.fail(RST_ERR_INVALID_ARG, "the tree lives on another device than the context");
+  if (n_queries == 0) return RST_OK;
+  CLOUD_TRY(k.begin());
+  const size_t n = (size_t)n_queries, kk = (size_t)k_nearest;
+  const size_t o_q = k.take(12 * n);
+  const size_t upload = k.off;
+  const size_t o_idx = k.take(4 * n * kk), o_d2 = k.take(4 * n * kk);
+  const size_t host_end = k.off;
+  CLOUD_TRY(k.commit(host_end));
+  std::memcpy(k.H + o_q, queries_xyz, 12 * n);
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.D, k.H, upload, cudaMemcpyHostToDevice, k.stream), "H2D"));
+  const Grid* d_grid = reinterpret_cast<const Grid*>(tree->d_mem + tree->o_grid);
+  const int* d_cs = reinterpret_cast<const int*>(tree->d_mem + tree->o_cs);
+  const float4* d_sorted = reinterpret_cast<const float4*>(tree->d_mem + tree->o_sorted);
+  if (k_nearest == 1)   // the search of FindCorrespondences / AlignIcp3d
+    k_nn_query<<<(unsigned)((n + 127) / 128), 128, 0, k.stream>>>(d_grid, d_cs, d_sorted, reinterpret_cast<const float*>(k.D + o_q), (int)n,
+                                                                    reinterpret_cast<int*>(k.D + o_idx), reinterpret_cast<float*>(k.D + o_d2));
+  else
+    k_knn_query<<<(unsigned)((n + 127) / 128), 128, 0, k.stream>>>(d_grid, d_cs, d_sorted, tree->m, reinterpret_cast<const float*>(k.D + o_q), (int)n,
+                                                                     k_nearest, reinterpret_cast<int*>(k.D + o_idx), reinterpret_cast<float*>(k.D + o_d2));
+  CLOUD_TRY(k.cuda(cudaGetLastError(), "launch"));
+  rst::ctx_count_launches(c, 1);
+  CLOUD_TRY(k.cuda(cudaMemcpyAsync(k.H + o_idx, k.D + o_idx, host_end - o_idx, cudaMemcpyDeviceToHost, k.stream), "D2H"));
+  CLOUD_TRY(k.cuda(cudaStreamSynchronize(k.stream), "sync"));
+  std::memcpy(indices_out, k.H + o_idx, 4 * n * kk);
+  std::memcpy(sq_dist_out, k.H + o_d2, 4 * n * kk);
   return RST_OK;
 }
 

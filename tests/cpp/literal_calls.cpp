@@ -181,6 +181,28 @@ int main() {
       if (!(cost >= 0.f) || !std::isfinite(cost) || !(e7 < e3 + 1e-3f)) ++failures;
     }
 
+    // kdtree.hpp:51-57 on the device-resident tree: dst_tree.query(p.data(), 1, &j, &dist_sqr) (align_icp.cpp:112) and k = 4
+    {
+      const rs_tracker::KDTree3f dst_tree{std::cref(dst_cloud), 16};
+      rs_tracker::GpuKDTree3f gpu_tree(rs_tracker::DefaultAlignContext(), dst_cloud);
+      int bad_q = gpu_tree.size() != n;
+      for (int i = 0; i < n; i += 211) {
+        int j = -1, gj[4], cj[4];
+        float dist_sqr = 0.f, gd[4], cd[4];
+        gpu_tree.query(s + 3 * i, 1, &j, &dist_sqr);
+        dst_tree.query(s + 3 * i, 1, cj, cd);
+        if (j != cj[0] || dist_sqr != cd[0]) ++bad_q;
+        gpu_tree.query(s + 3 * i, 4, gj, gd);
+        dst_tree.query(s + 3 * i, 4, cj, cd);
+        for (int e = 0; e < 4; ++e) if (gj[e] != cj[e] || gd[e] != cd[e]) ++bad_q;
+      }
+      std::vector<int> all_idx;
+      std::vector<float> all_d2;
+      if (!gpu_tree.query(src_cloud, 2, &all_idx, &all_d2) || (int)all_idx.size() != 2 * n) ++bad_q;
+      std::printf("GpuKDTree3f::query: %d mismatches against the k-d tree\n", bad_q);
+      if (bad_q) ++failures;
+    }
+
     // point_cloud_utils.cpp:26-32
     {
       Eigen::AlignedBox3f box;

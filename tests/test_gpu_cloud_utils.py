@@ -135,3 +135,51 @@ def test_compute_extents(al):
     lo, hi = al.cloud_extents(bad)
     keep = np.delete(GOLD["src"], 11, axis=0)
     assert np.array_equal(lo, keep.min(axis=0)) and np.array_equal(hi, keep.max(axis=0))     # NaN coordinates are ignored
+
+
+def brute_knn(target, queries, k):
+    """(d2, index)-ordered k nearest neighbours with nanoflann's fp32 accumulation ((dx^2 + dy^2) + dz^2)."""
+    t, q = target.astype(np.float32), queries.astype(np.float32)
+    d = q[:, None, :] - t[None, :, :]
+    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    order = np.lexsort((np.broadcast_to(np.arange(len(t)), d2.shape), d2), axis=1)[:, :k]
+    return order.astype(np.int32), np.take_along_axis(d2, order, axis=1)
+
+
+def test_tree_handle_knn_queries(al):
+    """KDTree3f built once, queried many times (kdtree.hpp:26-57): k = 1 is FindCorrespondences bit for bit; k > 1 is the
+    brute-force (distance, index) order with bit-identical squared distances; short clouds and non-finite queries pad
+    with -1 / +inf; the handle survives other calls on the context."""
+    tgt, src = GOLD["dst"], GOLD["src"]
+    tree = al.tree_create(tgt)
+    try:
+        idx1, d21 = al.tree_query(tree, src, 1)
+        idx_f, d2_f = al.find_correspondences(tgt, src)
+        assert np.array_equal(idx1[:, 0], idx_f) and np.array_equal(d21[:, 0], d2_f)
+        al.cloud_normals(depth_cloud(0), 16)                     # re-lays the context's arenas: the tree has its own memory
+        far = src[:64] * 3.0 + 5.0                               # queries well outside the cloud's box
+        for q, k in ((src, 5), (src[:200], 16), (src[:50], 33), (far, 8), (tgt[:100], 2)):
+            idx, d2 = al.tree_query(tree, q, k)
+            bi, bd = brute_knn(tgt, q, k)
+            assert np.array_equal(d2, bd)
+            same = idx == bi
+            assert same.mean() > 0.999 and np.array_equal(d2[~same], bd[~same])      # exact distance ties only
+        idx, d2 = al.tree_query(tree, tgt[:100], 2)
+        assert np.array_equal(idx[:, 0], np.arange(100)) and (d2[:, 0] == 0).all()   # a cloud point's nearest is itself
+        q = src[:8].copy(); q[2, 1] = np.nan; q[5] = np.inf
+        idx, d2 = al.tree_query(tree, q, 4)
+        assert (idx[[2, 5]] == -1).all() and np.isinf(d2[[2, 5]]).all() and (idx[[0, 1, 3, 4, 6, 7]] >= 0).all()
+    finally:
+        al.tree_destroy(tree)
+    small = al.tree_create(tgt[:3])
+    try:
+        idx, d2 = al.tree_query(small, src[:10], 5)
+        bi, bd = brute_knn(tgt[:3], src[:10], 3)
+        assert np.array_equal(idx[:, :3], bi) and np.array_equal(d2[:, :3], bd)
+        assert (idx[:, 3:] == -1).all() and np.isinf(d2[:, 3:]).all()
+        with pytest.raises(Exception):
+            al.tree_query(small, src[:10], 34)
+    finally:
+        al.tree_destroy(small)
+    with pytest.raises(Exception):
+        al.tree_create(np.zeros((0, 3), np.float32))
