@@ -65,3 +65,53 @@ def test_reference_call_sites_run_on_the_gpu():
         pytest.skip("oracle/_ref/literal_calls was not built (needs the reference tree at build time)")
     res = subprocess.run([str(LITERAL)], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "failures 0" in res.stdout, res.stdout + res.stderr
+
+
+def test_every_literal_signature_instantiates_against_the_stand_in_types(tmp_path):
+    """Every context-free signature of align_rgbd.hpp (align_icp.hpp:14-24, point_cloud_utils.hpp:9-31 + ComputeExtents,
+    align_gicp.hpp:15-25) and GpuKDTree3f, instantiated with the stand-in Cloud3f of oracle/shim and a tree type of the
+    reference's shape (kdtree.hpp: public `m_cloud` reference wrapper). Compile + link only: runs where neither the
+    reference tree nor a GPU exists; tests/cpp/literal_calls.cpp is the version against the reference's own types.hpp."""
+    src = tmp_path / "lit.cpp"
+    src.write_text(r'''
+#include <functional>
+#include <memory>
+#include <cho_util/core/geometry/point_cloud.hpp>
+#include "rs_tracker/align/align_rgbd.hpp"
+#ifndef RS_TRACKER_HAVE_EIGEN
+#error "Eigen signatures not enabled"
+#endif
+using Cloud3f = cho::core::PointCloud<float, 3>;
+struct Tree3f { explicit Tree3f(const std::reference_wrapper<const Cloud3f>& c, int = 10) : m_cloud(c) {} const std::reference_wrapper<const Cloud3f> m_cloud; };
+float all(const Cloud3f& src, const Cloud3f& dst) {
+  Eigen::Isometry3f xfm = Eigen::Isometry3f::Identity(), seed = xfm;
+  const Tree3f tree{std::cref(dst), 16};
+  std::vector<std::pair<int, int>> pairs; std::vector<float> weights, d2; std::vector<int> idx;
+  std::vector<Eigen::Matrix3f> sc, dc;
+  Cloud3f out, normals; Eigen::Vector3f centroid; Eigen::AlignedBox3f box;
+  bool ok = rs_tracker::SolveKabsch(src, dst, pairs, weights, &xfm);
+  ok = rs_tracker::AlignIcp3d(src, dst, 128, &xfm) && ok;
+  ok = rs_tracker::AlignIcp3d(src, dst, tree, 128, &xfm) && ok;
+  rs_tracker::DownsampleVoxel(src, 0.05f, &out);
+  rs_tracker::RemoveNans(src, &out);
+  rs_tracker::FindCorrespondences(tree, src, &idx, &d2);
+  rs_tracker::ComputeCentroid(src, &centroid);
+  rs_tracker::ComputeExtents(src, &box);
+  rs_tracker::ComputeCovariances(tree, dst, &dc, false);
+  rs_tracker::ComputeCovariances(tree, src, &sc, true);
+  rs_tracker::ComputeNormals(dst, tree, 16, &normals);
+  rs_tracker::OrientNormals(dst, Eigen::Vector3f(0.f, 0.f, 1.f), &normals);
+  float cost = rs_tracker::ComputeAlignment(src, dst, sc, dc, idx, seed, &xfm);
+  cost += rs_tracker::ComputeAlignment(src, dst, &xfm);
+  rs_tracker::GpuKDTree3f gpu_tree(rs_tracker::DefaultAlignContext(), dst);
+  int j; float d; gpu_tree.query(src.GetPtr(), 1, &j, &d);
+  gpu_tree.query(src, 4, &idx, &d2);
+  return ok ? cost : -1.f;
+}
+int main() { return 0; }
+''')
+    exe = tmp_path / "lit"
+    res = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-I", str(ROOT / "include"), "-I", str(ROOT / "oracle" / "shim"), str(src),
+                          "-L", str(ROOT / "realsensetracker_b200" / "_lib"), "-lrst_align",
+                          "-Wl,-rpath," + str(ROOT / "realsensetracker_b200" / "_lib"), "-o", str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
