@@ -255,7 +255,8 @@ inline void ComputeNormals(AlignContext& ctx, const Cloud& cloud, const float nu
   const rst_cloud c{cloud.GetPtr(), static_cast<std::int32_t>(cloud.GetNumPoints())};
   const float origin[3] = {0.f, 0.f, 0.f};
   normals->SetNumPoints(c.n);
-  if (c.n) rst_cloud_normals(ctx.get(), &c, static_cast<std::int32_t>(num_neighbors), origin, /*grid_cell=*/0.f, normals->GetPtr());
+  if (c.n && rst_cloud_normals(ctx.get(), &c, static_cast<std::int32_t>(num_neighbors), origin, /*grid_cell=*/0.f, normals->GetPtr()) != RST_OK)
+    normals->SetNumPoints(0);   // e.g. num_neighbors outside [2, 32]: no normals rather than unwritten ones (ctx.LastError() says why)
 }
 
 /// void OrientNormals(cloud, viewpoint, &normals)  point_cloud_utils.cpp:205-216; viewpoint_xyz: 3 floats.
