@@ -225,6 +225,26 @@ def centroid(pts):
     return c
 
 
+def extents(pts):
+    """ComputeExtents (point_cloud_utils.cpp:26-32): (lo [3], hi [3]); Eigen's empty box for an empty cloud."""
+    p = _f32(pts).reshape(-1, 3)
+    fmax = np.finfo(np.float32).max
+    if len(p) == 0:
+        return np.full(3, fmax, np.float32), np.full(3, -fmax, np.float32)
+    return p.min(axis=0), p.max(axis=0)
+
+
+def orient_normals(pts, viewpoint, normals):
+    """OrientNormals (point_cloud_utils.cpp:205-216): normal i is negated where (p_i - viewpoint) . n_i > 0; fp32, the
+    three products summed left to right without contraction (how the oracle's and the compiled reference's build
+    evaluate Eigen's dot). Returns a copy."""
+    p, n = _f32(pts).reshape(-1, 3), np.array(normals, dtype=np.float32, order="C", copy=True).reshape(-1, 3)
+    ray = p - _f32(viewpoint).reshape(1, 3)
+    dot = (ray[:, 0] * n[:, 0] + ray[:, 1] * n[:, 1]) + ray[:, 2] * n[:, 2]
+    n[dot > 0] *= np.float32(-1)
+    return n
+
+
 def remove_nans(pts):
     p = _f32(pts)
     out = np.empty_like(p)

@@ -61,6 +61,23 @@ def test_cloud_utilities_match():
     assert np.array_equal(idx_r, idx_o) and np.array_equal(d2_r, d2_o)
 
 
+def test_extents_and_orient_normals_match():
+    """ComputeExtents (point_cloud_utils.cpp:26-32) and OrientNormals (:205-216) through the reference's own code vs the
+    numpy restatements: bit for bit."""
+    rng = np.random.default_rng(3)
+    for cloud in (GOLD["src"], GOLD["dst"][:1], (rng.normal(size=(5000, 3)) * 3).astype(np.float32)):
+        (lo_r, hi_r), (lo_o, hi_o) = O.ref_extents(cloud), O.extents(cloud)
+        assert np.array_equal(lo_r, lo_o) and np.array_equal(hi_r, hi_o)
+        nrm = rng.normal(size=cloud.shape).astype(np.float32)
+        nrm[0] = 0.0
+        for vp in ((0.0, 0.0, 0.0), (0.3, -0.2, 1.5)):
+            got = O.ref_orient_normals(cloud, vp, nrm)
+            assert np.array_equal(got, O.orient_normals(cloud, vp, nrm))
+            assert (((cloud.astype(np.float64) - np.asarray(vp)) * got).sum(1) <= 1e-5).all()
+    lo, hi = O.extents(np.zeros((0, 3), np.float32))
+    assert (lo > 3e38).all() and (hi < -3e38).all()
+
+
 def test_reference_normals_follow_the_orientation_rule():
     """ComputeNormals + OrientNormals (point_cloud_utils.cpp:176-216): the convention the CUDA normal
     kernel inherits — n . (p - viewpoint) <= 0 — on a plane seen from the origin."""
