@@ -138,6 +138,11 @@ def test_gpu_gicp_minimize_over_fixed_correspondences():
         x0, x1 = np.linalg.norm(gn_step(st0)), np.linalg.norm(gn_step(st_at))
         print(f"gicp minimise: cost {st0.cost:.4f} -> {st1.cost:.4f}, Gauss-Newton step {x0:.2e} -> {x1:.2e}")
         assert x1 < 1e-3 and x1 < 0.2 * x0
+        # against the float64 CPU restatement of the same minimisation (same covariances and correspondences)
+        To, cost_o, _ = O.gicp_minimize(s, d, Cs, Cd, idx, T0=I, max_iters=32, huber=0.5)
+        assert abs(st1.cost - cost_o) <= 1e-3 * cost_o, (st1.cost, cost_o)
+        dt, dr = synth.pose_error(T1, To)
+        assert dt < 1e-3 and dr < 1e-3, (dt, dr)
         T2, st2 = al.gicp_minimize(s, d, Cs, Cd, idx, T0=I, max_iters=32)
         assert np.array_equal(T1, T2) and st2.cost == st1.cost             # deterministic
         # the 3-argument form = this call inside the correspondence loop
@@ -150,3 +155,24 @@ def test_gpu_gicp_minimize_over_fixed_correspondences():
         assert dt < 1e-3 and dr < 1e-3, (dt, dr)
     finally:
         al.close()
+
+
+def test_gicp_minimize_restatement_and_the_recorded_gpu_run():
+    """Oracle: Levenberg-Marquardt over gicp_evaluate's normal equations reaches a stationary point of the Huber GICP cost
+    on the golden clouds, and the costs are the ones the CUDA path printed on the B200
+    (profiles/r02_gicp_minimize_gpu_test.log: the -s output of test_gpu_gicp_minimize_over_fixed_correspondences)."""
+    import re
+    s, d = clouds()
+    Cs, Cd = O.covariances(s, True), O.covariances(d, True)
+    idx, _ = O.nn(d, s)
+    T, cost, hist = O.gicp_minimize(s, d, Cs, Cd, idx, max_iters=32)
+    assert all(b <= a for a, b in zip(hist, hist[1:])) and cost < 0.1 * hist[0]
+    r = O.gicp_evaluate(s, d, Cs, Cd, idx, T, huber=0.5)
+    A = np.zeros((6, 6)); A[np.triu_indices(6)] = r["A"]; A = A + A.T - np.diag(np.diag(A))
+    assert np.linalg.norm(np.linalg.solve(A, -r["b"])) < 1e-7
+    et, er = synth.pose_error(T, GN["gt"][0])
+    assert et < 5e-3 and er < 5e-3                               # one round of correspondences from the identity
+    log = (ROOT / "profiles" / "r02_gicp_minimize_gpu_test.log").read_text()
+    m = re.search(r"gicp minimise: cost ([0-9.]+) -> ([0-9.]+)", log)
+    assert m, "the recorded GPU line is missing"
+    assert abs(float(m.group(1)) - hist[0]) <= 2e-4 * hist[0] and abs(float(m.group(2)) - cost) <= 2e-4 * cost
