@@ -72,6 +72,23 @@ def test_null_and_bad_arguments_are_rejected_without_a_device():
     assert lib.rst_sync(None) == N.RST_ERR_INVALID_ARG
     assert lib.rst_launch_count(None) == 0
     lib.rst_ctx_destroy(None)  # must be a no-op
+    # the cloud entry points need a context as well: no context, no answer (and no CPU path behind them)
+    cloud = N.Cloud(None, 0)
+    buf = (C.c_float * 16)()
+    n = C.c_int32(0)
+    tree = C.c_void_p()
+    assert lib.rst_cloud_centroid(None, C.byref(cloud), buf) == N.RST_ERR_INVALID_ARG
+    assert lib.rst_cloud_extents(None, C.byref(cloud), buf, buf) == N.RST_ERR_INVALID_ARG
+    assert lib.rst_orient_normals(None, C.byref(cloud), buf, buf) == N.RST_ERR_INVALID_ARG
+    assert lib.rst_find_correspondences(None, C.byref(cloud), C.byref(cloud), 0.0, None, None) == N.RST_ERR_INVALID_ARG
+    assert lib.rst_cloud_covariances(None, C.byref(cloud), 0, 0.0, buf) == N.RST_ERR_INVALID_ARG
+    assert lib.rst_downsample_voxel(None, C.byref(cloud), 0.05, buf, C.byref(n)) == N.RST_ERR_INVALID_ARG
+    assert lib.rst_remove_nans(None, C.byref(cloud), buf, C.byref(n)) == N.RST_ERR_INVALID_ARG
+    assert lib.rst_tree_create(None, C.byref(cloud), 0.0, C.byref(tree)) == N.RST_ERR_INVALID_ARG and not tree.value
+    assert lib.rst_tree_query(None, None, buf, 1, 1, None, None) == N.RST_ERR_INVALID_ARG
+    assert lib.rst_tree_size(None) == 0
+    lib.rst_tree_destroy(None)  # no-op
+    assert lib.rst_gicp_minimize(None, C.byref(cloud), C.byref(cloud), buf, buf, None, 4, 0.5, buf, None) == N.RST_ERR_INVALID_ARG
 
 
 def test_product_never_imports_the_oracle():
